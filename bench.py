@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/sec of the transformer() hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one decode step (one token) of the named workload: one pass of the hot path
+(llama2.ts:205-303) over one batch.  Default workload: Llama-2-7B architecture, random-init
+fp32, batch-1 greedy decode (BASELINE.json configs[3], the configuration the north_star
+target "batch-1 decode at >= 70% of the HBM roofline" is quoted on).
+
+  value      tokens/s, device-resident greedy loop (inputs in HBM), CUDA-event time on the
+             library's stream, max over ranks.
+  e2e        tokens/s through the C ABI with HOST buffers: one l2b_forward_argmax(token,pos)
+             per token (token+pos copied in from pinned memory, the chosen token copied out),
+             wall clock between device synchronisations, max over ranks.
+  roofline   dominant kernel (w1/w3 matvec + SwiGLU): algorithmic bytes / CUDA-event time per
+             launch, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle (port of the reference forward, oracle/l2ref.c) on 1 host
+             thread -- the reference is single-threaded JS -- over the first tokens.
+
+N > 1: every rank runs its own independent sequence on its own GPU (weights replicated, no
+data-path collective) -- weak scaling; value = N * K tokens / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_weights_on_gpu(pkg, ctx, hdr, seed, device, keep_host=False):
+    """Random-init weights generated on the GPU (torch = plumbing) and handed to l2b_upload.
+    keep_host=True also returns the checkpoint as one float32 host blob (file order) for the
+    CPU oracle."""
+    import torch
+    blob = None
+    off = 0
+    if keep_host:
+        blob = np.empty(pkg.synth.weight_floats(hdr), dtype=np.float32)
+    for t, l, shape in pkg.synth.tensor_plan(hdr):
+        a = pkg.synth.gen_tensor_torch(hdr, t, l, seed, device).contiguous()
+        ctx.upload(t, l, a)
+        if keep_host:
+            n = a.numel()
+            blob[off:off + n] = a.flatten().cpu().numpy()
+            off += n
+        del a
+    torch.cuda.synchronize()
+    return blob
+
+
+def host_blob(pkg, hdr, seed):
+    """Checkpoint blob for the reference arm: GPU generation when a GPU is there (fast),
+    numpy otherwise."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            blob = np.empty(pkg.synth.weight_floats(hdr), dtype=np.float32)
+            off = 0
+            for t, l, shape in pkg.synth.tensor_plan(hdr):
+                a = pkg.synth.gen_tensor_torch(hdr, t, l, seed, "cuda:0")
+                n = a.numel()
+                blob[off:off + n] = a.flatten().cpu().numpy()
+                off += n
+            return blob
+    except Exception:
+        pass
+    return pkg.synth.checkpoint_blob(hdr, seed)[1]
+
+
+def host_mem_ok(n_bytes):
+    """True when the host (and its cgroup) can hold n_bytes more without risk."""
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except Exception:
+        return False
+    try:
+        mx = open("/sys/fs/cgroup/memory.max").read().strip()
+        cur = int(open("/sys/fs/cgroup/memory.current").read().strip())
+        if mx != "max":
+            avail = min(avail, int(mx) - cur)
+    except Exception:
+        pass
+    return avail is not None and avail > 1.6 * n_bytes + (8 << 30)
+
+
+def cpu_sample(oracle, hdr, blob, threads, budget_s, max_tokens, warm=0):
+    """Times the oracle's decode loop on `threads` host threads; stops at budget_s."""
+    m = oracle.Model(hdr, blob)
+    oracle.set_threads(threads)
+    V = abs(hdr[5])
+    tok = 1
+    for p in range(warm):
+        tok = int(np.argmax(m.forward(tok, p))) or 2
+    n, t0 = 0, time.perf_counter()
+    while n < max_tokens and n + warm < hdr[6]:
+        lg = m.forward(tok, warm + n)
+        tok = int(np.argmax(lg))
+        if tok == 1:
+            tok = 2
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    oracle.set_threads(1)
+    return n / dt, n, dt
+
+
+def run_workload(pkg, name, device, steps, warmup, seed, want_profile, keep_host=False):
+    """Returns dict with device-loop and e2e timings for one batch-1 workload on this rank."""
+    import torch
+    hdr = pkg.synth.header(name)
+    S = hdr[6]
+    rows = min(S, warmup + steps)
+    ctx = pkg.Context(hdr, device=device, max_batch=1, max_steps=rows)
+    blob = build_weights_on_gpu(pkg, ctx, hdr, seed, "cuda:%d" % device, keep_host)
+    out = {"hdr": hdr, "ctx": ctx, "blob": blob, "rows": rows}
+
+    def loop_device(n, pos0, tok0):
+        """n tokens of the device-resident greedy loop, wrapping at the KV capacity."""
+        ms, launches, done, tok, pos = 0.0, 0, 0, tok0, pos0
+        while done < n:
+            chunk = min(n - done, rows - pos)
+            toks = ctx.generate_greedy([tok], [pos], chunk)
+            ms += ctx.last_device_ms()
+            launches += ctx.last_launches()
+            tok = int(toks[-1, 0])
+            if tok == 1:
+                tok = 2
+            done += chunk
+            pos = (pos + chunk) % rows
+        return ms, launches, tok, pos
+
+    _, _, tok, pos = loop_device(warmup, 0, 1)
+    out["after_warmup"] = (tok, pos)
+    return out, loop_device
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="llama2-7b")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="key=value for l2b_set_option")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import llama2_ts_b200 as pkg
+    from oracle import l2ref as oracle  # checker / CPU baseline only
+
+    hdr = pkg.synth.header(args.workload)
+    base_cfg = {"workload": "%s architecture, random-init fp32, batch-1 greedy decode (-t 0), "
+                            "%d tokens/rank" % (args.workload, args.steps),
+                "dim": hdr[0], "hidden_dim": hdr[1], "n_layers": hdr[2], "n_heads": hdr[3],
+                "vocab": abs(hdr[5]), "batch_per_gpu": 1,
+                "parallelism": "independent sequences per GPU (weights replicated, no collective)",
+                "l2": "inputs larger than L2" if pkg.synth.weight_bytes_per_token(hdr) > 126e6
+                      else "weights fit the 126 MB L2 (L2-resident; HBM fraction is nominal)"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        oracle.build()
+        threads = oracle.max_threads()
+        if not host_mem_ok(4 * pkg.synth.weight_floats(hdr)):
+            print(json.dumps({"impl": "reference", "unavailable": "host memory too small for the "
+                              "%.1f GB checkpoint" % (4e-9 * pkg.synth.weight_floats(hdr))}))
+            return 0
+        blob = host_blob(pkg, hdr, args.seed)
+        budget = 90.0
+        warm = 1
+        tps, n, dt = cpu_sample(oracle, hdr, blob, threads, budget, args.steps, warm=warm)
+        line = {"impl": "reference", "metric": "decode tokens/sec", "value": tps, "unit": "tokens/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 / tps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 storage, f64 accumulate", "data": "synthetic",
+                "config": base_cfg,
+                "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                 "sample": "oracle/l2ref.c (C port of llama2.ts:205-303; no JS runtime "
+                                           "in the image), matmul rows split over %d host threads "
+                                           "(bit-identical to 1 thread), %d warm-up + %d timed tokens "
+                                           "from pos %d, %.1f s (time-capped at %.0f s)"
+                                           % (threads, warm, n, warm, dt, budget)},
+                "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    want_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    cpu_skip = None
+    if want_cpu and not host_mem_ok(4 * pkg.synth.weight_floats(hdr)):
+        want_cpu, cpu_skip = False, "host memory too small for a %.1f GB checkpoint copy" % (
+            4e-9 * pkg.synth.weight_floats(hdr))
+    st, loop_device = run_workload(pkg, args.workload, local_rank, args.steps, args.warmup,
+                                   args.seed + rank, True, keep_host=want_cpu)
+    ctx, rows = st["ctx"], st["rows"]
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    if args.opt:
+        loop_device(args.warmup, 0, 1)
+    tok, pos = st["after_warmup"]
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    # ---- timed region 1: device-resident loop, K tokens (inputs already in HBM)
+    barrier()
+    ms, launches, tok2, pos2 = loop_device(args.steps, pos, tok)
+    barrier()
+    ms = max_over_ranks(ms)
+    # ---- timed region 2: end to end through the C ABI, host buffers, one call per token
+    t_tok, t_pos = tok, pos
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nxt = ctx.forward_argmax(t_tok, t_pos)
+        t_tok = nxt if nxt != 1 else 2
+        t_pos = (t_pos + 1) % rows
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    # same, returning the full logits to the host (the temperature / top-p path)
+    lg = np.empty(abs(hdr[5]), dtype=np.float32)
+    n_lg = min(args.steps, 64)
+    t0 = time.perf_counter()
+    for _ in range(n_lg):
+        ctx.forward(t_tok, t_pos, lg)
+        t_tok = int(np.argmax(lg)) or 2
+        t_pos = (t_pos + 1) % rows
+    e2e_logits_s = (time.perf_counter() - t0) * args.steps / n_lg
+    clk = clocks.stop()
+
+    # ---- per-kernel CUDA-event times (no graph / PDL overlap), 4 steps mid-sequence
+    kms = np.zeros(pkg.capi.K_COUNT)
+    kn = np.zeros(pkg.capi.K_COUNT)
+    ppos = min(rows - 5, max(0, args.warmup + args.steps // 2))
+    for i in range(4):
+        a, b = ctx.profile_step(2 + i, ppos + i)
+        if i > 0:
+            kms += a
+            kn += b
+    D, F, L, H = hdr[:4]
+    V = abs(hdr[5])
+    kbytes = {pkg.capi.K_QKV: 4 * (3 * D * D + 2 * D + 3 * D),
+              pkg.capi.K_ATTN: 4 * (2 * (ppos + 2) * D + 2 * D),
+              pkg.capi.K_WO: 4 * (D * D + 3 * D),
+              pkg.capi.K_W13: 4 * (2 * F * D + 2 * D + F),
+              pkg.capi.K_W2: 4 * (D * F + F + 2 * D),
+              pkg.capi.K_CLS: 4 * (V * D + 2 * D + V)}
+    peak, peak_src = peaks()
+    per_kernel = {}
+    for k in range(pkg.capi.K_COUNT):
+        if kn[k] > 0:
+            avg_ms = kms[k] / kn[k]
+            per_kernel[pkg.capi.KERNEL_NAMES[k]] = {
+                "avg_us": round(1000 * avg_ms, 2), "launches_per_step": int(kn[k] / 3),
+                "bytes": kbytes[k], "gbs": round(kbytes[k] / (avg_ms * 1e-3) / 1e9, 1)}
+    dom = max(range(pkg.capi.K_COUNT), key=lambda k: kms[k])
+    dom_ms = kms[dom] / kn[dom]
+    achieved = kbytes[dom] / (dom_ms * 1e-3) / 1e9
+
+    n_tok = args.steps * world
+    value = n_tok / (ms * 1e-3)
+    mean_pos = (pos + (args.steps - 1) / 2.0) % rows
+    sbytes = pkg.synth.step_bytes(hdr, mean_pos)
+    line = {
+        "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 storage, f64 accumulate" if True else "f32", "data": "synthetic",
+        "config": base_cfg,
+        "e2e": {"value": n_tok / e2e_s, "unit": "tokens/s",
+                "h2d_bytes_per_step": 4 * (4 + 2), "d2h_bytes_per_step": 4,
+                "call": "l2b_forward_argmax(token,pos) per token (-t 0)",
+                "logits_variant_tokens_per_s": world * args.steps / e2e_logits_s,
+                "logits_variant_d2h_bytes_per_step": 4 * V},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": pkg.capi.KERNEL_NAMES[dom],
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": kbytes[dom],
+                     "avg_launch_us": 1000 * dom_ms,
+                     "step": {"bytes_per_token": sbytes, "achieved": sbytes / (ms / args.steps * 1e-3) / 1e9,
+                              "frac": sbytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+                              "roofline_tokens_per_s_per_gpu": peak * 1e9 / sbytes},
+                     "per_kernel": per_kernel},
+        "clocks": clk,
+    }
+
+    if want_cpu:
+        oracle.build()
+        tps, n, dt = cpu_sample(oracle, hdr, st["blob"], 1, 20.0, 4)
+        # parity spot-check of the very workload being timed (first token, full size)
+        ctx.reset()
+        got = ctx.forward(1, 0)
+        want = oracle.Model(hdr, st["blob"])
+        oracle.set_threads(oracle.max_threads())
+        ref = want.forward(1, 0)
+        oracle.set_threads(1)
+        line["cpu_baseline"] = {
+            "value": tps, "unit": "tokens/s", "cores": 1, "kind": "port",
+            "sample": "oracle/l2ref.c (C port of the reference forward; the reference is one JS "
+                      "thread and no JS runtime exists in the image), first %d tokens of this "
+                      "workload, %.1f s" % (n, dt),
+            "parity_vs_gpu_max_abs_logit_diff": float(np.max(np.abs(got - ref))),
+            "parity_bit_identical_frac": float(np.mean(got == ref))}
+    elif rank == 0:
+        line["cpu_baseline"] = {"value": None, "skipped": cpu_skip or "N > 1 or --no-cpu-baseline"}
+    ctx.close()
+
+    if rank == 0 and world == 1 and not args.no_others:
+        others = {}
+        for name in ("stories15M", "stories42M", "stories110M"):
+            if name == args.workload:
+                continue
+            try:
+                h2 = pkg.synth.header(name)
+                k2 = min(args.steps, h2[6] - args.warmup)
+                st2, loop2 = run_workload(pkg, name, local_rank, k2, args.warmup, args.seed, False)
+                t2, p2 = st2["after_warmup"]
+                torch.cuda.synchronize()
+                ms2, _, _, _ = loop2(k2, p2, t2)
+                b2 = pkg.synth.step_bytes(h2, p2 + (k2 - 1) / 2.0)
+                others[name] = {"tokens_per_s": k2 / (ms2 * 1e-3), "ms_per_step": ms2 / k2,
+                                "hbm_frac_nominal": b2 / (ms2 / k2 * 1e-3) / 1e9 / peak,
+                                "l2_resident": pkg.synth.weight_bytes_per_token(h2) < 126e6}
+                st2["ctx"].close()
+            except Exception as e:  # never lose the headline line to a side measurement
+                others[name] = {"error": str(e)}
+        line["others"] = others
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

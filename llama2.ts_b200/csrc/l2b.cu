@@ -1,0 +1,841 @@
+// l2b.cu -- host side of libllama2_b200.so: the C ABI declared in
+// include/llama2_b200.h.  Owns every device allocation (weights, RunState, KV
+// cache), the launch sequence of one decode step (llama2.ts:205-303), its CUDA
+// graph, and the device-resident greedy loop (llama2.ts:465-508).
+//
+// There is NO CPU implementation in this library: without a CUDA device
+// l2b_create fails with L2B_ECUDA.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/llama2_b200.h"
+#include "decode_kernels.cuh"
+
+#define L2B_API extern "C" __attribute__((visibility("default")))
+
+using namespace l2b;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Options {
+  int graph = 1;
+  int pdl = 1;
+  int f64 = 1;
+  int threads = 512;
+  int ctas_per_sm = 1;
+  int attn_cluster = 0;  // 0 = auto
+  int evict_first = -1;  // -1 = auto (weights > L2)
+};
+
+}  // namespace
+
+struct l2b_ctx {
+  // config (llama2.ts:69-93)
+  int D = 0, F = 0, L = 0, H = 0, hs = 0, V = 0, S = 0;
+  bool shared_cls = false;
+  int device = 0, num_sms = 148;
+  int Bmax = 1, steps = 0;
+  // tensor parallel
+  int tp_rank = 0, tp_size = 1;
+  // weights
+  float *tok_emb = nullptr, *rms_att = nullptr, *wqkv = nullptr, *wo = nullptr, *rms_ffn = nullptr,
+        *w13 = nullptr, *w2 = nullptr, *rms_final = nullptr, *fcr = nullptr, *fci = nullptr,
+        *wcls = nullptr;
+  std::vector<unsigned char> uploaded;  // [L2B_T_COUNT][L]
+  size_t weight_bytes = 0;
+  // run state (llama2.ts:131-163), all on the device
+  float *x = nullptr, *xb = nullptr, *q = nullptr, *hb = nullptr, *logits = nullptr;
+  float *kc = nullptr, *vc = nullptr;
+  int *d_ctl = nullptr, *d_dev = nullptr;  // host-written header / device-only {ticket,next[B]}
+  float* blk_val = nullptr;
+  int* blk_idx = nullptr;
+  int *d_forced = nullptr, *d_out = nullptr;
+  // host staging (pinned)
+  int* h_ctl = nullptr;
+  float* h_logits = nullptr;
+  int* h_out = nullptr;
+  std::vector<int> n_run;  // positions already run per sequence
+  // execution
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::map<int, cudaGraphExec_t> graphs;      // key: B
+  std::map<int, int> graph_launches;          // kernel nodes per step, key: B
+  std::set<const void*> smem_set;
+  Options opt;
+  float last_ms = 0.f;
+  int64_t last_launches = 0;
+  int64_t launch_counter = 0;
+  // per-class timing (l2b_profile_step)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_class;
+  std::string err;
+};
+
+namespace {
+
+int fail(l2b_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  g_create_error = buf;
+  return code;
+}
+
+#define CU(c, expr)                                                                        \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail((c), L2B_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+template <typename T>
+int dev_alloc(l2b_ctx* c, T** p, size_t count, bool zero) {
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    *p = nullptr;
+    cudaGetLastError();
+    return fail(c, e == cudaErrorMemoryAllocation ? L2B_ENOMEM : L2B_ECUDA,
+                "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  }
+  if (zero) {
+    e = cudaMemset(*p, 0, count * sizeof(T));
+    if (e != cudaSuccess) return fail(c, L2B_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+void drop_graphs(l2b_ctx* c) {
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+  c->graphs.clear();
+  c->graph_launches.clear();
+}
+
+// ---- kernel selection --------------------------------------------------------
+typedef void (*gemv_fn)(const GemvParams);
+
+template <int PRO, int EPI>
+gemv_fn pick_gemv(int nb, int threads, bool f64) {
+#define L2B_PICK(NB_, T_)                                             \
+  if (nb == NB_ && threads == T_)                                     \
+    return f64 ? (gemv_fn)gemv_pairs_kernel<PRO, EPI, NB_, T_, true>  \
+               : (gemv_fn)gemv_pairs_kernel<PRO, EPI, NB_, T_, false>;
+  L2B_PICK(1, 256)
+  L2B_PICK(1, 512)
+  L2B_PICK(2, 256)
+  L2B_PICK(2, 512)
+  L2B_PICK(4, 256)
+  L2B_PICK(8, 256)
+#undef L2B_PICK
+  return nullptr;
+}
+
+gemv_fn pick_kernel(int kc, int nb, int threads, bool f64) {
+  switch (kc) {
+    case L2B_K_QKV: return pick_gemv<PRO_RMS, EPI_QKV>(nb, threads, f64);
+    case L2B_K_WO:
+    case L2B_K_W2: return pick_gemv<PRO_COPY, EPI_RESID>(nb, threads, f64);
+    case L2B_K_W13: return pick_gemv<PRO_RMS, EPI_SWIGLU>(nb, threads, f64);
+    case L2B_K_CLS: return pick_gemv<PRO_RMS, EPI_LOGITS>(nb, threads, f64);
+  }
+  return nullptr;
+}
+
+int launch(l2b_ctx* c, int kclass, const void* fn, dim3 grid, dim3 block, size_t smem,
+           int cluster_x, void** args, cudaStream_t st) {
+  if (!c->smem_set.count(fn)) {
+    CU(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    c->smem_set.insert(fn);
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  memset(attrs, 0, sizeof attrs);
+  int na = 0;
+  if (cluster_x > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = cluster_x;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (c->opt.pdl && !c->profiling) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  if (c->profiling) {
+    cudaEvent_t e;
+    CU(c, cudaEventCreate(&e));
+    CU(c, cudaEventRecord(e, st));
+    c->prof_events.push_back(e);
+    c->prof_class.push_back(kclass);
+  }
+  CU(c, cudaLaunchKernelExC(&cfg, fn, args));
+  c->launch_counter++;
+  return 0;
+}
+
+int pick_nb(const l2b_ctx* c, int B, int n) {
+  int nb = 1;
+  while (nb < B && nb < kMaxNB) nb *= 2;
+  const size_t per = c->opt.f64 ? (size_t)n * 8 : (size_t)n * 4;
+  while (nb > 1 && nb * per > 200 * 1024) nb /= 2;
+  return nb;
+}
+
+int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
+  const int nb = pick_nb(c, B, p.n);
+  int threads = c->opt.threads;
+  if (nb >= 4) threads = 256;
+  gemv_fn fn = pick_kernel(kclass, nb, threads, c->opt.f64 != 0);
+  if (!fn) return fail(c, L2B_EINVAL, "no gemv kernel for nb=%d threads=%d", nb, threads);
+  const size_t per = c->opt.f64 ? (size_t)p.n * 8 : (size_t)p.n * 4;
+  int cps = c->opt.ctas_per_sm;
+  if (threads > 256 || nb > 2 || cps < 1) cps = 1;
+  if (cps * nb * per > 200 * 1024) cps = 1;
+  const int grid = c->num_sms * cps;
+  p.B = B;
+  for (int b0 = 0; b0 < B; b0 += nb) {
+    p.b0 = b0;
+    p.nact = (B - b0) < nb ? (B - b0) : nb;
+    void* args[] = {&p};
+    int rc = launch(c, kclass, (const void*)fn, dim3(grid), dim3(threads), nb * per, 1, args, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int auto_cluster(const l2b_ctx* c, int B) {
+  if (c->opt.attn_cluster > 0) return c->opt.attn_cluster;
+  int cs = 8;
+  while (cs > 1 && c->H * B * cs > c->num_sms) cs >>= 1;
+  return cs;
+}
+
+// One decode step for B sequences: tokens/positions are read from d_ctl.
+int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
+  const int D = c->D, F = c->F, hs = c->hs, H = c->H;
+  const size_t kv_seq = (size_t)H * c->steps * hs;
+  const size_t kv_layer = kv_seq * c->Bmax;
+  int ef = c->opt.evict_first;
+  if (ef < 0) ef = c->weight_bytes > (size_t)100 * 1024 * 1024;
+
+  GemvParams base;
+  memset(&base, 0, sizeof base);
+  base.tokp = c->d_ctl + CTL_HDR;
+  base.posp = c->d_ctl + CTL_HDR + B;
+  base.x = c->x;
+  base.xdim = D;
+  base.fcr = c->fcr;
+  base.fci = c->fci;
+  base.hs = hs;
+  base.steps = c->steps;
+  base.kv_seq_stride = (long long)kv_seq;
+  base.ctl = c->d_ctl;
+  base.ticket = c->d_dev;
+  base.next = c->d_dev + 1;
+  base.forced = c->d_forced;
+  base.out_tokens = c->d_out;
+  base.blk_val = c->blk_val;
+  base.blk_idx = c->blk_idx;
+  base.evict_first = ef;
+
+  const int cs = auto_cluster(c, B);
+  for (int l = 0; l < c->L; ++l) {
+    {  // rmsnorm -> q,k,v -> RoPE -> KV write   (llama2.ts:216-240)
+      GemvParams p = base;
+      p.W = c->wqkv + (size_t)l * 3 * D * D;
+      p.rows = 3 * D;
+      p.n = D;
+      p.vin = c->x;
+      p.vin_stride = D;
+      p.rms_w = c->rms_att + (size_t)l * D;
+      p.tok_emb = (l == 0) ? c->tok_emb : nullptr;
+      p.q = c->q;
+      p.kc = c->kc + (size_t)l * kv_layer;
+      p.vc = c->vc + (size_t)l * kv_layer;
+      p.Dq = D;
+      int rc = launch_gemv(c, L2B_K_QKV, p, B, st);
+      if (rc) return rc;
+    }
+    {  // attention (llama2.ts:244-267)
+      AttnParams a;
+      memset(&a, 0, sizeof a);
+      a.q = c->q;
+      a.kc = c->kc + (size_t)l * kv_layer;
+      a.vc = c->vc + (size_t)l * kv_layer;
+      a.xb = c->xb;
+      a.posp = c->d_ctl + CTL_HDR + B;
+      a.H = H;
+      a.hs = hs;
+      a.steps = c->steps;
+      a.q_stride = D;
+      a.xb_stride = D;
+      a.xb_off = 0;
+      a.tileT = kAttnStageBytes / (hs * 4);
+      a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
+      a.peer_xb = nullptr;
+      a.tp_size = 1;
+      const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
+      void* args[] = {&a};
+      int rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B),
+                      dim3(kAttnThreads), smem, cs, args, st);
+      if (rc) return rc;
+    }
+    {  // wo matvec + residual (llama2.ts:270-273)
+      GemvParams p = base;
+      p.W = c->wo + (size_t)l * D * D;
+      p.rows = D;
+      p.n = D;
+      p.vin = c->xb;
+      p.vin_stride = D;
+      int rc = launch_gemv(c, L2B_K_WO, p, B, st);
+      if (rc) return rc;
+    }
+    {  // rmsnorm -> w1,w3 -> SwiGLU (llama2.ts:276-289)
+      GemvParams p = base;
+      p.W = c->w13 + (size_t)l * 2 * F * D;
+      p.rows = 2 * F;
+      p.n = D;
+      p.vin = c->x;
+      p.vin_stride = D;
+      p.rms_w = c->rms_ffn + (size_t)l * D;
+      p.hb = c->hb;
+      p.hb_stride = F;
+      int rc = launch_gemv(c, L2B_K_W13, p, B, st);
+      if (rc) return rc;
+    }
+    {  // w2 matvec + residual (llama2.ts:292-295)
+      GemvParams p = base;
+      p.W = c->w2 + (size_t)l * D * F;
+      p.rows = D;
+      p.n = F;
+      p.vin = c->hb;
+      p.vin_stride = F;
+      int rc = launch_gemv(c, L2B_K_W2, p, B, st);
+      if (rc) return rc;
+    }
+  }
+  {  // final rmsnorm -> classifier -> argmax (llama2.ts:299-302, 364-366)
+    GemvParams p = base;
+    p.W = c->wcls;
+    p.rows = c->V;
+    p.n = D;
+    p.vin = c->x;
+    p.vin_stride = D;
+    p.rms_w = c->rms_final;
+    p.logits = c->logits;
+    p.V = c->V;
+    int rc = launch_gemv(c, L2B_K_CLS, p, B, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// Runs `n_steps` decode steps for B sequences, graph-launched when enabled.
+// Events ev0/ev1 bracket the device work on the ctx stream.
+int run_steps(l2b_ctx* c, int B, int n_steps) {
+  const int64_t l0 = c->launch_counter;
+  const bool use_graph = c->opt.graph != 0 && !c->profiling;
+  cudaGraphExec_t ge = nullptr;
+  if (use_graph) {
+    auto it = c->graphs.find(B);
+    if (it == c->graphs.end()) {
+      cudaGraph_t g = nullptr;
+      const int64_t before = c->launch_counter;
+      cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) return fail(c, L2B_ECUDA, "begin capture: %s", cudaGetErrorString(e));
+      int rc = enqueue_step(c, B, c->stream);
+      e = cudaStreamEndCapture(c->stream, &g);
+      const int per_step = (int)(c->launch_counter - before);
+      c->launch_counter = before;
+      if (rc) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc;
+      }
+      if (e != cudaSuccess) return fail(c, L2B_ECUDA, "end capture: %s", cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&ge, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) return fail(c, L2B_ECUDA, "graph instantiate: %s", cudaGetErrorString(e));
+      c->graphs[B] = ge;
+      c->graph_launches[B] = per_step;
+    } else {
+      ge = it->second;
+    }
+  }
+  CU(c, cudaEventRecord(c->ev0, c->stream));
+  if (use_graph) {
+    for (int s = 0; s < n_steps; ++s) CU(c, cudaGraphLaunch(ge, c->stream));
+    c->launch_counter += (int64_t)n_steps * c->graph_launches[B];
+  } else {
+    for (int s = 0; s < n_steps; ++s) {
+      int rc = enqueue_step(c, B, c->stream);
+      if (rc) return rc;
+    }
+  }
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  c->last_launches = c->launch_counter - l0;
+  return 0;
+}
+
+int finish(l2b_ctx* c) {
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  return 0;
+}
+
+int check_ready(l2b_ctx* c) {
+  if (!c) return L2B_EINVAL;
+  if (!l2b_weights_ready(c)) return fail(c, L2B_ESTATE, "weights not fully uploaded");
+  return 0;
+}
+
+// Validates (token,pos) of sequence b and fills the pinned header.
+int stage_inputs(l2b_ctx* c, int B, const int32_t* tokens, const int32_t* pos, int step0,
+                 int use_forced, int advance, int n_steps) {
+  if (B < 1 || B > c->Bmax) return fail(c, L2B_EINVAL, "B=%d outside [1,%d]", B, c->Bmax);
+  if (!tokens || !pos) return fail(c, L2B_EINVAL, "null tokens/pos");
+  for (int b = 0; b < B; ++b) {
+    if (tokens[b] < 0 || tokens[b] >= c->V)
+      return fail(c, L2B_EINVAL, "token %d of sequence %d outside [0,%d)", tokens[b], b, c->V);
+    if (pos[b] < 0 || pos[b] + n_steps > c->steps)
+      return fail(c, L2B_EINVAL, "pos %d (+%d steps) of sequence %d outside the %d cached rows",
+                  pos[b], n_steps, b, c->steps);
+    if (pos[b] > c->n_run[b])
+      return fail(c, L2B_EORDER, "pos %d of sequence %d called before positions %d..%d were run",
+                  pos[b], b, c->n_run[b], pos[b] - 1);
+  }
+  c->h_ctl[CTL_STEP] = step0;
+  c->h_ctl[CTL_USE_FORCED] = use_forced;
+  c->h_ctl[CTL_ADVANCE] = advance;
+  c->h_ctl[CTL_RESERVED] = 0;
+  for (int b = 0; b < B; ++b) {
+    c->h_ctl[CTL_HDR + b] = tokens[b];
+    c->h_ctl[CTL_HDR + B + b] = pos[b];
+  }
+  CU(c, cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(int) * (CTL_HDR + 2 * B), cudaMemcpyHostToDevice,
+                        c->stream));
+  return 0;
+}
+
+void mark_run(l2b_ctx* c, int B, const int32_t* pos, int n_steps) {
+  for (int b = 0; b < B; ++b)
+    if (pos[b] + n_steps > c->n_run[b]) c->n_run[b] = pos[b] + n_steps;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+
+L2B_API int l2b_abi_version(void) { return L2B_ABI_VERSION; }
+
+L2B_API const char* l2b_last_error(const l2b_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch, int32_t max_steps,
+                         int32_t tp_rank, int32_t tp_size, l2b_ctx** out) {
+  if (!hdr || !out) return fail(nullptr, L2B_EINVAL, "null hdr/out");
+  *out = nullptr;
+  const int D = hdr[0], F = hdr[1], L = hdr[2], H = hdr[3];
+  const int V = hdr[5] < 0 ? -hdr[5] : hdr[5], S = hdr[6];
+  if (D <= 0 || F <= 0 || L <= 0 || H <= 0 || V <= 0 || S <= 0)
+    return fail(nullptr, L2B_EINVAL, "non-positive config field");
+  if (D % H != 0) return fail(nullptr, L2B_EINVAL, "dim %d not divisible by n_heads %d", D, H);
+  const int hs = D / H;
+  if (D % 4 || F % 4 || hs % 4 || (V & 1))
+    return fail(nullptr, L2B_EINVAL,
+                "kernels need dim, hidden_dim, head_size multiples of 4 and an even vocab");
+  if (hs > kAttnMaxHs) return fail(nullptr, L2B_EINVAL, "head_size %d > %d", hs, kAttnMaxHs);
+  if (max_batch < 1) return fail(nullptr, L2B_EINVAL, "max_batch must be >= 1");
+  if (max_steps < 0 || max_steps > S) return fail(nullptr, L2B_EINVAL, "max_steps outside [0,seq_len]");
+  if (max_steps == 0) max_steps = S;
+  if (tp_size != 1) return fail(nullptr, L2B_EINVAL, "tensor parallel degree %d not supported", tp_size);
+  (void)tp_rank;
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, L2B_ECUDA, "no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, L2B_EINVAL, "device %d of %d", device, ndev);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, L2B_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, L2B_ECUDA, "device properties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, L2B_ECUDA, "device is sm_%d%d; this library is built for sm_100a only",
+                prop.major, prop.minor);
+
+  l2b_ctx* c = new l2b_ctx();
+  c->D = D; c->F = F; c->L = L; c->H = H; c->hs = hs; c->V = V; c->S = S;
+  c->shared_cls = hdr[5] > 0;
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->Bmax = max_batch;
+  c->steps = max_steps;
+  c->uploaded.assign((size_t)L2B_T_COUNT * L, 0);
+  c->n_run.assign(max_batch, 0);
+
+  int rc = 0;
+#define TRY(x) if (!rc) rc = (x)
+  const size_t sD = D, sF = F, sL = L, sV = V, sS = S, sB = max_batch;
+  TRY(dev_alloc(c, &c->tok_emb, sV * sD, false));
+  TRY(dev_alloc(c, &c->rms_att, sL * sD, false));
+  TRY(dev_alloc(c, &c->wqkv, sL * 3 * sD * sD, false));
+  TRY(dev_alloc(c, &c->wo, sL * sD * sD, false));
+  TRY(dev_alloc(c, &c->rms_ffn, sL * sD, false));
+  TRY(dev_alloc(c, &c->w13, sL * 2 * sF * sD, false));
+  TRY(dev_alloc(c, &c->w2, sL * sD * sF, false));
+  TRY(dev_alloc(c, &c->rms_final, sD, false));
+  TRY(dev_alloc(c, &c->fcr, sS * (hs / 2), false));
+  TRY(dev_alloc(c, &c->fci, sS * (hs / 2), false));
+  if (c->shared_cls) {
+    c->wcls = c->tok_emb;  // llama2.ts:127
+  } else {
+    TRY(dev_alloc(c, &c->wcls, sV * sD, false));
+  }
+  c->weight_bytes = 4 * (sL * (4 * sD * sD + 3 * sD * sF + 2 * sD) + sD + sV * sD);
+  TRY(dev_alloc(c, &c->x, sB * sD, true));
+  TRY(dev_alloc(c, &c->xb, sB * sD, true));
+  TRY(dev_alloc(c, &c->q, sB * sD, true));
+  TRY(dev_alloc(c, &c->hb, sB * sF, true));
+  TRY(dev_alloc(c, &c->logits, sB * sV, true));
+  const size_t kv = sL * sB * sD * (size_t)max_steps;
+  TRY(dev_alloc(c, &c->kc, kv, true));
+  TRY(dev_alloc(c, &c->vc, kv, true));
+  TRY(dev_alloc(c, &c->d_ctl, CTL_HDR + 2 * sB, true));
+  TRY(dev_alloc(c, &c->d_dev, 1 + sB, true));
+  const size_t max_grid = (size_t)c->num_sms * 4;
+  TRY(dev_alloc(c, &c->blk_val, max_grid * kMaxNB, true));
+  TRY(dev_alloc(c, &c->blk_idx, max_grid * kMaxNB, true));
+  TRY(dev_alloc(c, &c->d_forced, (size_t)max_steps * sB, true));
+  TRY(dev_alloc(c, &c->d_out, (size_t)max_steps * sB, true));
+#undef TRY
+  if (!rc) {
+    cudaError_t e2 = cudaMallocHost((void**)&c->h_ctl, sizeof(int) * (CTL_HDR + 2 * sB));
+    if (e2 == cudaSuccess) e2 = cudaMallocHost((void**)&c->h_logits, sizeof(float) * sB * sV);
+    if (e2 == cudaSuccess) e2 = cudaMallocHost((void**)&c->h_out, sizeof(int) * (size_t)max_steps * sB);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev0);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev1);
+    if (e2 != cudaSuccess) rc = fail(c, L2B_ECUDA, "host/stream setup: %s", cudaGetErrorString(e2));
+  }
+  if (rc) {
+    g_create_error = c->err;
+    l2b_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return L2B_OK;
+}
+
+L2B_API int l2b_create(const int32_t hdr[7], int32_t device, int32_t max_batch, int32_t max_steps,
+                       l2b_ctx** out) {
+  return create_common(hdr, device, max_batch, max_steps, 0, 1, out);
+}
+
+L2B_API int l2b_create_tp(const int32_t hdr[7], int32_t device, int32_t max_steps, int32_t tp_rank,
+                          int32_t tp_size, l2b_ctx** out) {
+  return create_common(hdr, device, 1, max_steps, tp_rank, tp_size, out);
+}
+
+L2B_API void l2b_destroy(l2b_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  float* fl[] = {c->tok_emb, c->rms_att, c->wqkv, c->wo, c->rms_ffn, c->w13, c->w2, c->rms_final,
+                 c->fcr, c->fci, c->shared_cls ? nullptr : c->wcls, c->x, c->xb, c->q, c->hb,
+                 c->logits, c->kc, c->vc, c->blk_val};
+  for (float* p : fl)
+    if (p) cudaFree(p);
+  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out};
+  for (int* p : il)
+    if (p) cudaFree(p);
+  if (c->h_ctl) cudaFreeHost(c->h_ctl);
+  if (c->h_logits) cudaFreeHost(c->h_logits);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float* host,
+                       uint64_t n_floats) {
+  if (!c) return L2B_EINVAL;
+  if (!host) return fail(c, L2B_EINVAL, "null host pointer");
+  if (tensor_id < 0 || tensor_id >= L2B_T_COUNT) return fail(c, L2B_EINVAL, "tensor id %d", tensor_id);
+  const size_t D = c->D, F = c->F, V = c->V, S = c->S, hs2 = c->hs / 2;
+  const bool layered = (tensor_id >= L2B_T_RMS_ATT_WEIGHT && tensor_id <= L2B_T_W3);
+  if (layer < 0 || layer >= (layered ? c->L : 1))
+    return fail(c, L2B_EINVAL, "layer %d out of range for tensor %d", layer, tensor_id);
+  CU(c, cudaSetDevice(c->device));
+  size_t expect = 0;
+  float* dst = nullptr;
+  switch (tensor_id) {
+    case L2B_T_TOKEN_EMBEDDING_TABLE: expect = V * D; dst = c->tok_emb; break;
+    case L2B_T_RMS_ATT_WEIGHT: expect = D; dst = c->rms_att + layer * D; break;
+    case L2B_T_WQ: expect = D * D; dst = c->wqkv + (size_t)layer * 3 * D * D; break;
+    case L2B_T_WK: expect = D * D; dst = c->wqkv + (size_t)layer * 3 * D * D + D * D; break;
+    case L2B_T_WV: expect = D * D; dst = c->wqkv + (size_t)layer * 3 * D * D + 2 * D * D; break;
+    case L2B_T_WO: expect = D * D; dst = c->wo + (size_t)layer * D * D; break;
+    case L2B_T_RMS_FFN_WEIGHT: expect = D; dst = c->rms_ffn + layer * D; break;
+    case L2B_T_W1: expect = F * D; dst = c->w13 + (size_t)layer * 2 * F * D; break;
+    case L2B_T_W3: expect = F * D; dst = c->w13 + (size_t)layer * 2 * F * D + D; break;
+    case L2B_T_W2: expect = D * F; dst = c->w2 + (size_t)layer * D * F; break;
+    case L2B_T_RMS_FINAL_WEIGHT: expect = D; dst = c->rms_final; break;
+    case L2B_T_FREQ_CIS_REAL: expect = S * hs2; dst = c->fcr; break;
+    case L2B_T_FREQ_CIS_IMAG: expect = S * hs2; dst = c->fci; break;
+    case L2B_T_WCLS:
+      if (c->shared_cls)
+        return fail(c, L2B_ESTATE, "shared classifier: wcls aliases the embedding table (llama2.ts:127)");
+      expect = V * D; dst = c->wcls; break;
+  }
+  if (n_floats != expect)
+    return fail(c, L2B_EINVAL, "tensor %d expects %zu floats, got %llu", tensor_id, expect,
+                (unsigned long long)n_floats);
+  // make sure no step is still reading the old contents
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (tensor_id == L2B_T_W1 || tensor_id == L2B_T_W3) {
+    // interleave rows: device row 2i = w1 row i, 2i+1 = w3 row i (pairs feed SwiGLU)
+    CU(c, cudaMemcpy2D(dst, 2 * D * sizeof(float), host, D * sizeof(float), D * sizeof(float), F,
+                       cudaMemcpyDefault));
+  } else {
+    CU(c, cudaMemcpy(dst, host, expect * sizeof(float), cudaMemcpyDefault));
+  }
+  c->uploaded[(size_t)tensor_id * c->L + layer] = 1;
+  return L2B_OK;
+}
+
+L2B_API int l2b_weights_ready(const l2b_ctx* c) {
+  if (!c) return 0;
+  for (int t = 0; t < L2B_T_COUNT; ++t) {
+    const bool layered = (t >= L2B_T_RMS_ATT_WEIGHT && t <= L2B_T_W3);
+    if (t == L2B_T_WCLS && c->shared_cls) continue;
+    const int n = layered ? c->L : 1;
+    for (int l = 0; l < n; ++l)
+      if (!c->uploaded[(size_t)t * c->L + l]) return 0;
+  }
+  return 1;
+}
+
+L2B_API int l2b_forward_batch(l2b_ctx* c, int32_t B, const int32_t* tokens, const int32_t* pos,
+                              float* logits_out, int32_t* argmax_out) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  CU(c, cudaSetDevice(c->device));
+  rc = stage_inputs(c, B, tokens, pos, 0, 0, 0, 1);
+  if (rc) return rc;
+  rc = run_steps(c, B, 1);
+  if (rc) return rc;
+  if (logits_out)
+    CU(c, cudaMemcpyAsync(c->h_logits, c->logits, sizeof(float) * (size_t)B * c->V,
+                          cudaMemcpyDeviceToHost, c->stream));
+  if (argmax_out)
+    CU(c, cudaMemcpyAsync(c->h_out, c->d_dev + 1, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
+  rc = finish(c);
+  if (rc) return rc;
+  if (logits_out) memcpy(logits_out, c->h_logits, sizeof(float) * (size_t)B * c->V);
+  if (argmax_out) memcpy(argmax_out, c->h_out, sizeof(int) * B);
+  mark_run(c, B, pos, 1);
+  return L2B_OK;
+}
+
+L2B_API int l2b_forward(l2b_ctx* c, int32_t token, int32_t pos, float* logits_out) {
+  if (c && !logits_out) return fail(c, L2B_EINVAL, "null logits_out");
+  return l2b_forward_batch(c, 1, &token, &pos, logits_out, nullptr);
+}
+
+L2B_API int l2b_forward_argmax(l2b_ctx* c, int32_t token, int32_t pos, int32_t* next_out) {
+  if (c && !next_out) return fail(c, L2B_EINVAL, "null next_out");
+  return l2b_forward_batch(c, 1, &token, &pos, nullptr, next_out);
+}
+
+L2B_API int l2b_generate_greedy(l2b_ctx* c, int32_t B, const int32_t* tokens, const int32_t* pos,
+                                int32_t n_steps, const int32_t* forced, int32_t* out_tokens) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (n_steps < 1 || !out_tokens) return fail(c, L2B_EINVAL, "n_steps < 1 or null out_tokens");
+  CU(c, cudaSetDevice(c->device));
+  rc = stage_inputs(c, B, tokens, pos, 0, forced != nullptr, 1, n_steps);
+  if (rc) return rc;
+  const size_t n = (size_t)n_steps * B;
+  if (forced) {
+    for (size_t i = 0; i < n; ++i)
+      if (forced[i] >= c->V) return fail(c, L2B_EINVAL, "forced token %d >= vocab", forced[i]);
+    memcpy(c->h_out, forced, sizeof(int) * n);
+    CU(c, cudaMemcpyAsync(c->d_forced, c->h_out, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // h_out is reused for the result below
+  }
+  rc = run_steps(c, B, n_steps);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->h_out, c->d_out, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  rc = finish(c);
+  if (rc) return rc;
+  memcpy(out_tokens, c->h_out, sizeof(int) * n);
+  mark_run(c, B, pos, n_steps);
+  return L2B_OK;
+}
+
+L2B_API float l2b_last_device_ms(const l2b_ctx* c) { return c ? c->last_ms : 0.f; }
+L2B_API int64_t l2b_last_launches(const l2b_ctx* c) { return c ? c->last_launches : 0; }
+
+L2B_API int l2b_profile_step(l2b_ctx* c, int32_t token, int32_t pos, float* ms_per_class,
+                             int32_t* launches_per_class) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!ms_per_class || !launches_per_class) return fail(c, L2B_EINVAL, "null output");
+  CU(c, cudaSetDevice(c->device));
+  rc = stage_inputs(c, 1, &token, &pos, 0, 0, 0, 1);
+  if (rc) return rc;
+  c->profiling = true;
+  c->prof_events.clear();
+  c->prof_class.clear();
+  rc = run_steps(c, 1, 1);
+  c->profiling = false;
+  if (!rc) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    c->prof_events.push_back(e);
+    rc = finish(c);
+  }
+  for (int k = 0; k < L2B_K_COUNT; ++k) {
+    ms_per_class[k] = 0.f;
+    launches_per_class[k] = 0;
+  }
+  if (!rc) {
+    for (size_t i = 0; i + 1 < c->prof_events.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]);
+      ms_per_class[c->prof_class[i]] += ms;
+      launches_per_class[c->prof_class[i]] += 1;
+    }
+    mark_run(c, 1, &pos, 1);
+  }
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  c->prof_events.clear();
+  c->prof_class.clear();
+  return rc;
+}
+
+L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer, int32_t pos,
+                           float* out, uint64_t n_floats) {
+  if (!c) return L2B_EINVAL;
+  if (!out) return fail(c, L2B_EINVAL, "null out");
+  if (seq < 0 || seq >= c->Bmax) return fail(c, L2B_EINVAL, "seq %d", seq);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const size_t D = c->D;
+  const float* src = nullptr;
+  size_t n = D;
+  switch (which) {
+    case L2B_S_X: src = c->x + seq * D; break;
+    case L2B_S_Q: src = c->q + seq * D; break;
+    case L2B_S_XB: src = c->xb + seq * D; break;
+    case L2B_S_HB: src = c->hb + (size_t)seq * c->F; n = c->F; break;
+    case L2B_S_LOGITS: src = c->logits + (size_t)seq * c->V; n = c->V; break;
+    case L2B_S_KEY_ROW:
+    case L2B_S_VALUE_ROW: {
+      if (layer < 0 || layer >= c->L || pos < 0 || pos >= c->steps)
+        return fail(c, L2B_EINVAL, "layer/pos out of range");
+      if (n_floats != D) return fail(c, L2B_EINVAL, "expected %zu floats", D);
+      const size_t kv_seq = (size_t)c->H * c->steps * c->hs;
+      const float* base = (which == L2B_S_KEY_ROW ? c->kc : c->vc) +
+                          ((size_t)layer * c->Bmax + seq) * kv_seq + (size_t)pos * c->hs;
+      // head-major [H][steps][hs] -> the reference's row [H*hs]
+      CU(c, cudaMemcpy2D(out, c->hs * sizeof(float), base, (size_t)c->steps * c->hs * sizeof(float),
+                         c->hs * sizeof(float), c->H, cudaMemcpyDeviceToHost));
+      return L2B_OK;
+    }
+    default: return fail(c, L2B_EINVAL, "which=%d", which);
+  }
+  if (n_floats != n) return fail(c, L2B_EINVAL, "expected %zu floats, got %llu", n,
+                                 (unsigned long long)n_floats);
+  CU(c, cudaMemcpy(out, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return L2B_OK;
+}
+
+L2B_API int l2b_reset(l2b_ctx* c) {
+  if (!c) return L2B_EINVAL;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const size_t kv = (size_t)c->L * c->Bmax * c->D * (size_t)c->steps;
+  CU(c, cudaMemset(c->kc, 0, kv * sizeof(float)));
+  CU(c, cudaMemset(c->vc, 0, kv * sizeof(float)));
+  for (int& v : c->n_run) v = 0;
+  return L2B_OK;
+}
+
+L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
+  if (!c || !key) return L2B_EINVAL;
+  Options& o = c->opt;
+  const std::string k(key);
+  const int v = (int)value;
+  if (k == "graph") o.graph = v != 0;
+  else if (k == "pdl") o.pdl = v != 0;
+  else if (k == "f64") o.f64 = v != 0;
+  else if (k == "threads") {
+    if (v != 256 && v != 512) return fail(c, L2B_EINVAL, "threads must be 256 or 512");
+    o.threads = v;
+  } else if (k == "ctas_per_sm") {
+    if (v < 1 || v > 2) return fail(c, L2B_EINVAL, "ctas_per_sm must be 1 or 2");
+    o.ctas_per_sm = v;
+  } else if (k == "attn_cluster") {
+    if (v != 0 && v != 1 && v != 2 && v != 4 && v != 8)
+      return fail(c, L2B_EINVAL, "attn_cluster must be 0,1,2,4,8");
+    o.attn_cluster = v;
+  } else if (k == "evict_first") {
+    o.evict_first = v < 0 ? -1 : (v != 0);
+  } else {
+    return fail(c, L2B_EINVAL, "unknown option '%s'", key);
+  }
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
+  return L2B_OK;
+}
+
+L2B_API int64_t l2b_tp_export(l2b_ctx* c, void* blob, uint64_t cap) {
+  (void)blob;
+  (void)cap;
+  return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
+}
+
+L2B_API int l2b_tp_connect(l2b_ctx* c, const void* blobs, uint64_t blob_bytes, int32_t n_ranks) {
+  (void)blobs;
+  (void)blob_bytes;
+  (void)n_ranks;
+  return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
+}
