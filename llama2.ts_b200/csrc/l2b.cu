@@ -159,7 +159,10 @@ gemv_fn pick_kernel(int kc, int nb, int threads, bool f64) {
 int launch(l2b_ctx* c, int kclass, const void* fn, dim3 grid, dim3 block, size_t smem,
            int cluster_x, void** args, cudaStream_t st) {
   if (!c->smem_set.count(fn)) {
-    CU(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cudaFuncAttributes fa;
+    CU(c, cudaFuncGetAttributes(&fa, fn));
+    const int max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;  // static smem counts too
+    CU(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
     c->smem_set.insert(fn);
   }
   cudaLaunchConfig_t cfg;

@@ -1,0 +1,104 @@
+"""Full-size checks on the Llama-2-7B architecture (BASELINE.json configs[3]): the oracle is
+run on the real 26.4 GB of random-init weights for a few positions (all host threads; rows
+split over threads give the same bits), plus size-independent properties over a longer run."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ATOL, RTOL = 1e-4, 1e-3
+
+
+def _mem_gb():
+    for ln in open("/proc/meminfo"):
+        if ln.startswith("MemAvailable:"):
+            return int(ln.split()[1]) / 1e6
+    return 0
+
+
+@pytest.mark.parametrize("cluster", [0, 4, 1])
+def test_wide_shapes(pkg, oracle, cluster):
+    """head_size 128 (one warp per cache row), multi-tile rows, F not a tile multiple."""
+    hdr = pkg.synth.header("wide")
+    _, blob = pkg.synth.checkpoint_blob(hdr, seed=31, std=0.03)
+    ref = oracle.Model(hdr, blob)
+    oracle.set_threads(oracle.max_threads())
+    toks = np.concatenate([[1], pkg.synth.teacher_tokens(63, 2048, 31)])
+    with pkg.Context(hdr, max_steps=64) as ctx:
+        pkg.synth.upload_blob(ctx, hdr, blob)
+        ctx.set_option("attn_cluster", cluster)
+        for pos in range(64):
+            got = ctx.forward(int(toks[pos]), pos)
+            want = ref.forward(int(toks[pos]), pos)
+            assert np.allclose(got, want, rtol=RTOL, atol=ATOL), (pos, np.abs(got - want).max())
+    oracle.set_threads(1)
+
+
+@pytest.fixture(scope="module")
+def seven_b(pkg):
+    import torch
+    hdr = pkg.synth.header("llama2-7b")
+    need = 4e-9 * pkg.synth.weight_floats(hdr)
+    if _mem_gb() < 1.6 * need + 8:
+        pytest.skip("host memory too small for the %.0f GB checkpoint copy" % need)
+    ctx = pkg.Context(hdr, device=0, max_batch=1, max_steps=300)
+    blob = np.empty(pkg.synth.weight_floats(hdr), dtype=np.float32)
+    off = 0
+    for t, l, shape in pkg.synth.tensor_plan(hdr):
+        a = pkg.synth.gen_tensor_torch(hdr, t, l, 5, "cuda:0").contiguous()
+        torch.cuda.synchronize()
+        ctx.upload(t, l, a)
+        n = a.numel()
+        blob[off:off + n] = a.flatten().cpu().numpy()
+        off += n
+    yield hdr, blob, ctx
+    ctx.close()
+
+
+def test_7b_logits_vs_oracle(pkg, oracle, seven_b):
+    hdr, blob, ctx = seven_b
+    ref = oracle.Model(hdr, blob)
+    oracle.set_threads(oracle.max_threads())
+    toks = [1, 9906, 1917, 29991]
+    try:
+        for pos, t in enumerate(toks):
+            got = ctx.forward(t, pos)
+            want = ref.forward(t, pos)
+            if not np.allclose(got, want, rtol=RTOL, atol=ATOL):
+                for l in range(hdr[2]):            # locate the first layer that diverges
+                    dk = np.abs(ctx.read_state(pkg.capi.S_KEY_ROW, 0, l, pos) - ref.key_row(l, pos)).max()
+                    dv = np.abs(ctx.read_state(pkg.capi.S_VALUE_ROW, 0, l, pos) - ref.value_row(l, pos)).max()
+                    print("layer %d: max|dK| %.3g max|dV| %.3g" % (l, dk, dv))
+                    if max(dk, dv) > 1e-3:
+                        break
+            assert np.allclose(got, want, rtol=RTOL, atol=ATOL), (pos, np.abs(got - want).max())
+            assert int(np.argmax(got)) == oracle.argmax(want)
+            print("7B pos %d: max|dlogit| %.3g, bit-identical %.2f%%" %
+                  (pos, np.abs(got - want).max(), 100 * np.mean(got == want)))
+    finally:
+        oracle.set_threads(1)
+
+
+def test_7b_properties_256_tokens(pkg, oracle, seven_b):
+    """Size-independent properties over a 256-token greedy run at full size:
+    determinism, device-loop == host-driven loop == graph-less launches, and the first-max
+    argmax of the returned logits equals the device argmax at every step."""
+    hdr, blob, ctx = seven_b
+    ctx.reset()
+    a = ctx.generate_greedy([1], [0], 256)[:, 0]
+    ctx.reset()
+    b = ctx.generate_greedy([1], [0], 256)[:, 0]
+    assert np.array_equal(a, b)
+    ctx.reset()
+    ctx.set_option("graph", 0)
+    ctx.set_option("pdl", 0)
+    tok, host = 1, []
+    lg = np.empty(32000, dtype=np.float32)
+    for pos in range(256):
+        ctx.forward(tok, pos, lg)
+        assert np.isfinite(lg).all()
+        nxt = oracle.argmax(lg)
+        host.append(nxt)
+        tok = nxt
+    ctx.set_option("graph", 1)
+    ctx.set_option("pdl", 1)
+    assert np.array_equal(np.array(host), a)
