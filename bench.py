@@ -35,6 +35,26 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full summary
+    (profiles/rNN_ncu_summary.json, newest round), or None."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json")), reverse=True):
+        try:
+            vals = []
+            for k in json.load(open(f)).get("ncu_set_full", []):
+                if k.get("kernel") == kernel:
+                    rd = k["dram__bytes_read.sum"].split()
+                    wr = k["dram__bytes_write.sum"].split()
+                    mul = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+                    vals.append(float(rd[0]) * mul[rd[1]] + float(wr[0]) * mul[wr[1]])
+            if vals:
+                return sum(vals) / len(vals)
+        except Exception:
+            pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -103,6 +123,7 @@ def build_weights_on_gpu(pkg, ctx, hdr, seed, device, keep_host=False):
         blob = np.empty(pkg.synth.weight_floats(hdr), dtype=np.float32)
     for t, l, shape in pkg.synth.tensor_plan(hdr):
         a = pkg.synth.gen_tensor_torch(hdr, t, l, seed, device).contiguous()
+        torch.cuda.synchronize()          # l2b_upload copies on its own stream
         ctx.upload(t, l, a)
         if keep_host:
             n = a.numel()
@@ -378,7 +399,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": pkg.capi.KERNEL_NAMES[dom],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src,
+                     "traffic": ncu_traffic(pkg.capi.KERNEL_NAMES[dom]) if args.workload == "llama2-7b" else None,
                      "algorithmic_bytes_per_launch": kbytes[dom],
                      "avg_launch_us": 1000 * dom_ms,
                      "step": {"bytes_per_token": sbytes, "achieved": sbytes / (ms / args.steps * 1e-3) / 1e9,

@@ -81,7 +81,8 @@ int l2b_create_tp(const int32_t hdr[7], int32_t device, int32_t max_steps,
 
 /* Replaces holding the Float32Array slices of readWeights() (llama2.ts:112-129).
  * COPIES n_floats from host into HBM (re-laid out for the kernels); the caller
- * may free `host` on return.  `layer` is the index into the per-layer arrays
+ * may free `host` on return.  `host` may also be a device pointer whose contents
+ * are complete (the copy is cudaMemcpyDefault on the ctx stream).  `layer` is the index into the per-layer arrays
  * (0 for the unlayered tensors).  L2B_T_WCLS must not be uploaded for a shared
  * classifier -- the library aliases the embedding table like llama2.ts:127.     */
 int l2b_upload(l2b_ctx* ctx, int32_t tensor_id, int32_t layer, const float* host,

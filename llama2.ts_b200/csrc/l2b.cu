@@ -552,6 +552,11 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev1);
     if (e2 != cudaSuccess) rc = fail(c, L2B_ECUDA, "host/stream setup: %s", cudaGetErrorString(e2));
   }
+  if (!rc) {
+    // the zero-fills above ran on the NULL stream; the ctx stream is non-blocking
+    cudaError_t e3 = cudaDeviceSynchronize();
+    if (e3 != cudaSuccess) rc = fail(c, L2B_ECUDA, "device sync: %s", cudaGetErrorString(e3));
+  }
   if (rc) {
     g_create_error = c->err;
     l2b_destroy(c);
@@ -632,11 +637,14 @@ L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float
   CU(c, cudaStreamSynchronize(c->stream));
   if (tensor_id == L2B_T_W1 || tensor_id == L2B_T_W3) {
     // interleave rows: device row 2i = w1 row i, 2i+1 = w3 row i (pairs feed SwiGLU)
-    CU(c, cudaMemcpy2D(dst, 2 * D * sizeof(float), host, D * sizeof(float), D * sizeof(float), F,
-                       cudaMemcpyDefault));
+    CU(c, cudaMemcpy2DAsync(dst, 2 * D * sizeof(float), host, D * sizeof(float), D * sizeof(float), F,
+                            cudaMemcpyDefault, c->stream));
   } else {
-    CU(c, cudaMemcpy(dst, host, expect * sizeof(float), cudaMemcpyDefault));
+    CU(c, cudaMemcpyAsync(dst, host, expect * sizeof(float), cudaMemcpyDefault, c->stream));
   }
+  // the copy runs on the ctx stream (device sources are asynchronous otherwise): the
+  // caller may free `host` on return and the next step sees the new contents
+  CU(c, cudaStreamSynchronize(c->stream));
   c->uploaded[(size_t)tensor_id * c->L + layer] = 1;
   return L2B_OK;
 }
@@ -795,8 +803,9 @@ L2B_API int l2b_reset(l2b_ctx* c) {
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->stream));
   const size_t kv = (size_t)c->L * c->Bmax * c->D * (size_t)c->steps;
-  CU(c, cudaMemset(c->kc, 0, kv * sizeof(float)));
-  CU(c, cudaMemset(c->vc, 0, kv * sizeof(float)));
+  CU(c, cudaMemsetAsync(c->kc, 0, kv * sizeof(float), c->stream));
+  CU(c, cudaMemsetAsync(c->vc, 0, kv * sizeof(float), c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   for (int& v : c->n_run) v = 0;
   return L2B_OK;
 }
