@@ -1,0 +1,478 @@
+// batch_gemm.cuh -- batched decode: B independent sequences turn every matmul()
+// of llama2.ts:196-203 into a dense GEMM  C[M][B] = W[M][K] * X[B][K]^T  that runs
+// on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// The reference computes in fp32 storage / f64 accumulation; a single TF32 pass
+// puts 10k-20k of 32000 logits outside the 1e-4 tolerance,
+// so every product is formed as the 3xTF32 split
+//       w*x ~= w_hi*x_hi + w_hi*x_lo + w_lo*x_hi        (fp32 accumulate in TMEM)
+// with  v_hi = v rounded to nearest at 10 mantissa bits (exactly representable in TF32) and
+// v_lo = v - v_hi (exact in fp32, |v_lo| <= 2^-11 |v|, symmetric in sign).
+//
+// The tensor core adds into its fp32 accumulator with truncation, a bias of ~half an ulp
+// per tcgen05.mma that grows with the length of the accumulation chain (measured: logits
+// error proportional to K per split).  Chains are kept short three ways: the two small
+// terms go to their own accumulator (its truncation error is 2^-11 smaller), the w_hi*x_hi
+// terms rotate over G "main" accumulators (TMEM has 512 columns: G = 7 for N <= 64, 3 for
+// N = 128, 1 for N = 256), and k is split over work items; all partial accumulators are
+// added with round-to-nearest fp32 in the epilogues.
+// Weights arrive ONCE from HBM as fp32 through TMA (SWIZZLE_128B tiles); four
+// "splitter" warps derive the hi/lo tiles in shared memory in place (an elementwise
+// rewrite, so the swizzled layout is preserved), the activations are pre-split by
+// the epilogue kernel that produced them.
+//
+// Warp roles of the 256-thread CTA (one CTA per SM, persistent over work items):
+//   warp 0      TMA producer   (cp.async.bulk.tensor, ring of `stages` stages)
+//   warp 1      MMA issuer     (one elected lane, 12 x tcgen05.mma per 32-float k-block)
+//   warp 2      TMEM allocator
+//   warps 4-7   splitter, then epilogue (tcgen05.ld -> partial sums in global memory)
+// A work item is (128-row tile of W, k-split); partial sums go to P[split][b][m] and
+// are reduced in a fixed order by the fused elementwise kernels at the end of this
+// file (RoPE + KV write, residual + rmsnorm, SwiGLU, logits + argmax), which also
+// emit the pre-split activations of the next GEMM.
+#pragma once
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "decode_kernels.cuh"
+
+namespace l2b {
+
+constexpr int kGemmThreads = 256;
+constexpr int kBM = 128;                    // weight rows per tile (UMMA M)
+constexpr int kBK = 32;                     // floats per k-block: one 128-byte swizzle row
+constexpr int kTileA = kBM * kBK * 4;       // 16 KB
+constexpr uint32_t kHiMask = 0xFFFFE000u;   // keeps sign, exponent and 10 mantissa bits (TF32)
+
+// round-to-nearest split v = hi + lo with hi exactly representable in TF32
+__device__ __forceinline__ uint32_t tf32_hi_bits(uint32_t bits) { return (bits + 0x1000u) & kHiMask; }
+
+struct GemmParams {
+  float* P;       // partial sums [S][B][M]
+  int M, K;       // weight rows, reduction length
+  int S;          // k splits
+  int B;          // sequences (columns) written out
+  int n0;         // first column of this launch (batches > 256 run in column groups)
+  int tiles_m;    // ceil(M / 128)
+  int kblocks;    // ceil(K / 32)
+  int stages;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], both operands K-major SWIZZLE_128B, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
+  const uint32_t a = smem_u32(smem);
+  return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// N = padded number of sequences handled by one MMA (UMMA N): 32, 64, 128 or 256
+template <int N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXh,
+                   const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ GemmParams p) {
+  constexpr int kTileX = N * kBK * 4;
+  constexpr int kStage = 2 * kTileA + 2 * kTileX;
+  constexpr int kMaxStages = 8;
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+  constexpr int G = N == 256 ? 1 : (N == 128 ? 3 : 7);           // main accumulators
+  constexpr uint32_t kTmemCols = (G + 1) * N <= 256 ? 256u : 512u;  // power of two >= (G+1)*N
+
+  extern __shared__ __align__(1024) unsigned char gsm[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], split_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  // dynamic shared memory is only guaranteed 16-byte aligned: round up to the swizzle atom
+  unsigned char* sm = gsm + ((1024u - (smem_u32(gsm) & 1023u)) & 1023u);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 4);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&tmem_empty_bar, 4);
+    mbar_fence_init();
+    tmap_prefetch(&tmW);
+    tmap_prefetch(&tmXh);
+    tmap_prefetch(&tmXl);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  griddep_wait();  // the activations X were written by the previous kernel
+
+  const int n_items = p.tiles_m * p.S;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int st = 0, ph = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int split = it / p.tiles_m, mt = it - split * p.tiles_m;
+        const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
+        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          unsigned char* base = sm + (size_t)st * kStage;
+          mbar_arrive_expect_tx(&full_bar[st], kTileA + 2 * kTileX);
+          tma_load_2d(base, &tmW, kb * kBK, mt * kBM, &full_bar[st]);
+          tma_load_2d(base + 2 * kTileA, &tmXh, kb * kBK, p.n0, &full_bar[st]);
+          tma_load_2d(base + 2 * kTileA + kTileX, &tmXl, kb * kBK, p.n0, &full_bar[st]);
+          if (++st == stages) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      int st = 0, ph = 0, li = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+        const int split = it / p.tiles_m;
+        const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
+        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
+        mbar_wait(&tmem_empty_bar, (li & 1) ^ 1);  // epilogue drained the accumulator
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int kk = kb - kb0;
+          const uint32_t d_small = tmem_base;                                  // columns [0, N)
+          const uint32_t d_main = tmem_base + (uint32_t)((1 + kk % G) * N);    // rotating main accumulator
+          const uint32_t acc_main = kk >= G ? 1u : 0u;
+          mbar_wait(&split_bar[st], ph);
+          tc_fence_after();
+          unsigned char* base = sm + (size_t)st * kStage;
+          const uint64_t dAh = umma_desc_sw128(base), dAl = umma_desc_sw128(base + kTileA);
+          const uint64_t dXh = umma_desc_sw128(base + 2 * kTileA);
+          const uint64_t dXl = umma_desc_sw128(base + 2 * kTileA + kTileX);
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 step
+            tc_mma_tf32(d_small, dAl + adv, dXh + adv, kIdesc, (kk | k) != 0 ? 1u : 0u);
+            tc_mma_tf32(d_small, dAh + adv, dXl + adv, kIdesc, 1u);
+            tc_mma_tf32(d_main, dAh + adv, dXh + adv, kIdesc, k != 0 ? 1u : acc_main);
+          }
+          tc_commit(&empty_bar[st]);  // frees the stage when these MMAs have read it
+          if (++st == stages) { st = 0; ph ^= 1; }
+        }
+        tc_commit(&tmem_full_bar);  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- splitter + epilogue ----------------
+    const int t = threadIdx.x - 128;  // 0..127
+    const int wq = warp & 3;          // TMEM lane quadrant this warp may read
+    int st = 0, ph = 0, li = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+      const int split = it / p.tiles_m, mt = it - split * p.tiles_m;
+      const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
+      const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[st], ph);
+        uint4* ah = reinterpret_cast<uint4*>(sm + (size_t)st * kStage);
+        uint4* al = reinterpret_cast<uint4*>(sm + (size_t)st * kStage + kTileA);
+#pragma unroll
+        for (int i = 0; i < kTileA / 16 / 128; ++i) {
+          const int c = t + i * 128;
+          const uint4 v = ah[c];
+          uint4 h, l;
+          h.x = tf32_hi_bits(v.x); h.y = tf32_hi_bits(v.y); h.z = tf32_hi_bits(v.z); h.w = tf32_hi_bits(v.w);
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          ah[c] = h;
+          al[c] = l;
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[st]);
+        if (++st == stages) { st = 0; ph ^= 1; }
+      }
+      // epilogue: TMEM -> registers -> P[split][b][m]
+      mbar_wait(&tmem_full_bar, li & 1);
+      tc_fence_after();
+      const int m = mt * kBM + wq * 32 + lane;
+      float* out = p.P + ((size_t)split * p.B + p.n0) * p.M + m;
+      const int used = (kb1 - kb0) < G ? (kb1 - kb0) : G;  // main accumulators written by this item
+      const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        if (p.n0 + c0 >= p.B) break;
+        uint32_t r[32];
+        float sum[32];
+        tmem_ld32(lane_base + (uint32_t)(N + c0), r);  // main accumulator 0
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
+#pragma unroll 1
+        for (int g = 1; g < used; ++g) {
+          tmem_ld32(lane_base + (uint32_t)((1 + g) * N + c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+        }
+        tmem_ld32(lane_base + (uint32_t)c0, r);  // small terms last
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+        if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (p.n0 + c0 + j < p.B) out[(size_t)(c0 + j) * p.M] = sum[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fused elementwise kernels between the GEMMs (CUDA cores; activations are tiny)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void store_split(float* xh, float* xl, size_t i, float v) {
+  const float h = __uint_as_float(tf32_hi_bits(__float_as_uint(v)));
+  xh[i] = h;
+  xl[i] = v - h;
+}
+
+struct BatVecParams {
+  const float* P;        // partial sums [S][B][M] or nullptr
+  int S, B, M;
+  const float* tok_emb;  // != nullptr: x := embedding row (llama2.ts:211)
+  const int* tokp;
+  float* x;              // [B][D]
+  const float* rms_w;    // rmsnorm weight of the NEXT projection
+  float* xh;             // [Bpad][D] pre-split normalised activations
+  float* xl;
+  int D;
+};
+
+// x += sum_s P[s][b][:]  (accum, llama2.ts:168-170)  or  x := emb[token];
+// then rmsnorm (llama2.ts:172-179) -> hi/lo split for the next GEMM.  One CTA per sequence.
+__global__ void __launch_bounds__(256) bat_resid_rms_kernel(const __grid_constant__ BatVecParams p) {
+  __shared__ double red[8];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int b = blockIdx.x, D = p.D;
+  float* x = p.x + (size_t)b * D;
+  double ss = 0.0;
+  for (int j = threadIdx.x; j < D; j += 256) {
+    float v;
+    if (p.tok_emb != nullptr) {
+      v = p.tok_emb[(size_t)ld_act_i32(p.tokp + b) * D + j];
+    } else {
+      float add = 0.f;
+      for (int s = 0; s < p.S; ++s) add += ld_act(p.P + ((size_t)s * p.B + b) * p.M + j);
+      v = (float)((double)ld_act(x + j) + (double)add);
+    }
+    x[j] = v;
+    ss += (double)v * (double)v;
+  }
+  ss = warp_sum_f64(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  tot /= (double)D;
+  tot = 1.0 / sqrt(1e-5 + tot);
+  for (int j = threadIdx.x; j < D; j += 256) {
+    const float o = (float)((double)__ldg(p.rms_w + j) * (tot * (double)x[j]));
+    store_split(p.xh, p.xl, (size_t)b * D + j, o);
+  }
+}
+
+struct BatQkvParams {
+  const float* P;  // [S][B][3D]
+  int S, B, D, hs, steps;
+  const int* posp;
+  const float* fcr;
+  const float* fci;
+  float* q;        // [B][D]
+  float* kc;       // layer base [B][H][steps][hs]
+  float* vc;
+  long long kv_seq_stride;
+};
+
+// RoPE (llama2.ts:224-235) + KV-cache write (:238-240); one thread per row pair.
+__global__ void __launch_bounds__(256) bat_qkv_epi_kernel(const __grid_constant__ BatQkvParams p) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int b = blockIdx.y;
+  const int pair = blockIdx.x * 256 + threadIdx.x;
+  const int M = 3 * p.D;
+  if (2 * pair >= M) return;
+  const int r = 2 * pair;
+  float s0 = 0.f, s1 = 0.f;
+  for (int s = 0; s < p.S; ++s) {
+    const float2 v = *reinterpret_cast<const float2*>(p.P + ((size_t)s * p.B + b) * M + r);
+    s0 += v.x;
+    s1 += v.y;
+  }
+  const int pos = ld_act_i32(p.posp + b);
+  const int seg = r / p.D, i = r - seg * p.D;
+  const int h = i / p.hs, c = i - h * p.hs;
+  const size_t row = (size_t)b * p.kv_seq_stride + ((size_t)h * p.steps + pos) * p.hs + c;
+  if (seg == 2) {
+    p.vc[row] = s0;
+    p.vc[row + 1] = s1;
+  } else {
+    const double fr = (double)__ldg(p.fcr + (size_t)pos * (p.hs / 2) + c / 2);
+    const double fi = (double)__ldg(p.fci + (size_t)pos * (p.hs / 2) + c / 2);
+    const float o0 = (float)((double)s0 * fr - (double)s1 * fi);
+    const float o1 = (float)((double)s0 * fi + (double)s1 * fr);
+    float* dst = seg == 0 ? p.q + (size_t)b * p.D + i : p.kc + row;
+    dst[0] = o0;
+    dst[1] = o1;
+  }
+}
+
+struct BatSwigluParams {
+  const float* P;  // [S][B][2F], rows interleaved (2i = w1 row i, 2i+1 = w3 row i)
+  int S, B, F;
+  float* xh;       // [Bpad][F]
+  float* xl;
+};
+
+// SwiGLU (llama2.ts:284-289) -> pre-split input of the w2 GEMM
+__global__ void __launch_bounds__(256) bat_swiglu_kernel(const __grid_constant__ BatSwigluParams p) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= p.F) return;
+  float h1 = 0.f, h3 = 0.f;
+  for (int s = 0; s < p.S; ++s) {
+    const float2 v = *reinterpret_cast<const float2*>(p.P + ((size_t)s * p.B + b) * (2 * (size_t)p.F) + 2 * i);
+    h1 += v.x;
+    h3 += v.y;
+  }
+  const double hv = (double)h1;
+  const float silu = (float)(hv * (1.0 / (1.0 + exp(-hv))));
+  store_split(p.xh, p.xl, (size_t)b * p.F + i, (float)((double)silu * (double)h3));
+}
+
+struct BatLogitsParams {
+  const float* P;  // [S][B][V]
+  int S, B, V;
+  float* logits;   // [B][V]
+  int* ctl;
+  int* next;
+  const int* forced;
+  int* out_tokens;
+};
+
+// logits (llama2.ts:302) + argmax (:364-366) + state advance (:471-504); one CTA per sequence
+__global__ void __launch_bounds__(1024) bat_logits_kernel(const __grid_constant__ BatLogitsParams p) {
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int b = blockIdx.x, V = p.V;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < V; j += 1024) {
+    float v = 0.f;
+    for (int s = 0; s < p.S; ++s) v += ld_act(p.P + ((size_t)s * p.B + b) * V + j);
+    p.logits[(size_t)b * V + j] = v;
+    argmax_consider(v, j, bv, bi);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    argmax_consider(ov, oi, bv, bi);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_v[threadIdx.x >> 5] = bv;
+    s_i[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w) argmax_consider(s_v[w], s_i[w], bv, bi);
+    const float l0 = p.logits[(size_t)b * V];
+    if (bi == 0x7fffffff || l0 != l0) bi = 0;
+    const int B = p.B;
+    const int step = ld_act_i32(p.ctl + CTL_STEP);
+    int chosen = bi;
+    if (ld_act_i32(p.ctl + CTL_USE_FORCED)) {
+      const int f = p.forced[(size_t)step * B + b];
+      if (f >= 0) chosen = f;
+    }
+    p.next[b] = bi;
+    p.out_tokens[(size_t)step * B + b] = chosen;
+    if (ld_act_i32(p.ctl + CTL_ADVANCE)) {
+      int* tok = p.ctl + CTL_HDR;
+      tok[b] = chosen;
+      tok[B + b] = tok[B + b] + 1;
+    }
+  }
+}
+
+// advances the step counter once every sequence has been handled (own launch: the
+// per-sequence CTAs above must all have read the old value first)
+__global__ void bat_step_kernel(int* ctl) {
+  griddep_launch_dependents();
+  griddep_wait();
+  if (threadIdx.x == 0 && ctl[CTL_ADVANCE]) ctl[CTL_STEP] = ctl[CTL_STEP] + 1;
+}
+
+}  // namespace l2b

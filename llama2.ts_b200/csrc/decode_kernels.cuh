@@ -474,6 +474,9 @@ struct AttnParams {
   // tensor-parallel all-gather of the output slice (nullptr when tp_size == 1)
   float* const* peer_xb;  // [tp_size] peers' xb buffers (including our own)
   int tp_size;
+  // batched tensor-core path: also emit the TF32 hi/lo split of the output (input of the wo GEMM)
+  float* xh;
+  float* xl;
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __grid_constant__ AttnParams p) {
@@ -672,6 +675,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
     float s = 0.f;
     for (uint32_t r = 0; r < CS; ++r) s += dsmem_ld_f32(dsmem_addr(&c_out[tid], r));
     const size_t o = (size_t)b * p.xb_stride + p.xb_off + (size_t)h * hs + tid;
+    if (p.xh != nullptr) {
+      const float hi = __uint_as_float((__float_as_uint(s) + 0x1000u) & 0xFFFFE000u);
+      p.xh[o] = hi;
+      p.xl[o] = s - hi;
+    }
     if (p.tp_size <= 1) {
       p.xb[o] = s;
     } else {

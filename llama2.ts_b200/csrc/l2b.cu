@@ -12,11 +12,13 @@
 #include <string.h>
 
 #include <map>
+#include <utility>
 #include <set>
 #include <string>
 #include <vector>
 
 #include "../../include/llama2_b200.h"
+#include "batch_gemm.cuh"
 #include "decode_kernels.cuh"
 
 #define L2B_API extern "C" __attribute__((visibility("default")))
@@ -35,6 +37,8 @@ struct Options {
   int ctas_per_sm = 1;
   int attn_cluster = 0;  // 0 = auto
   int evict_first = -1;  // -1 = auto (weights > L2)
+  int tc_min_batch = 9;  // batches >= this run the tcgen05 GEMM path (0 = never)
+  int tc_splits = 0;     // 0 = auto k-split per GEMM
 };
 
 }  // namespace
@@ -60,6 +64,10 @@ struct l2b_ctx {
   float* blk_val = nullptr;
   int* blk_idx = nullptr;
   int *d_forced = nullptr, *d_out = nullptr;
+  // batched tensor-core path: pre-split activations [256*groups][D or F], partial sums
+  float *XhD = nullptr, *XlD = nullptr, *XhF = nullptr, *XlF = nullptr, *P = nullptr;
+  int Bpad = 0, Smax = 4;
+  std::map<std::pair<const void*, int>, CUtensorMap> tmaps;  // key: (operand base, box rows)
   // host staging (pinned)
   int* h_ctl = nullptr;
   float* h_logits = nullptr;
@@ -237,8 +245,194 @@ int auto_cluster(const l2b_ctx* c, int B) {
   return cs;
 }
 
+// ---- batched tensor-core path --------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+// 2-D fp32 tensor map over a row-major [rows][K] matrix, box = 32 floats x box_rows, 128B swizzle
+int get_tmap(l2b_ctx* c, const float* base, size_t rows, size_t K, int box_rows, const CUtensorMap** out) {
+  const std::pair<const void*, int> key(base, box_rows);
+  auto it = c->tmaps.find(key);
+  if (it == c->tmaps.end()) {
+    static encode_tiled_fn enc = nullptr;
+    if (!enc) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      CU(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+      if (!fn || qr != cudaDriverEntryPointSuccess) return fail(c, L2B_ECUDA, "cuTensorMapEncodeTiled not found");
+      enc = (encode_tiled_fn)fn;
+    }
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, L2B_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    it = c->tmaps.emplace(key, tm).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+int gemm_n_for(int cols) { return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256; }
+
+// k-split so that (tiles x splits) fills whole waves of the 148 SMs without drowning the
+// step in partial-sum traffic
+int pick_splits(const l2b_ctx* c, int M, int K, int B) {
+  if (c->opt.tc_splits > 0) return c->opt.tc_splits < c->Smax ? c->opt.tc_splits : c->Smax;
+  const int tiles = (M + kBM - 1) / kBM, kblocks = (K + kBK - 1) / kBK;
+  double best = 1e30;
+  int best_s = 1;
+  for (int s = 1; s <= c->Smax && s * 4 <= kblocks; ++s) {
+    const int items = tiles * s;
+    const int waves = (items + c->num_sms - 1) / c->num_sms;
+    const double eff = (double)items / ((double)waves * c->num_sms);
+    const double bytes = (double)M * K * 4 / eff + (s > 1 ? 2.0 : 1.0) * s * (double)M * B * 4;
+    if (bytes < best) { best = bytes; best_s = s; }
+  }
+  return best_s;
+}
+
+int launch_gemm(l2b_ctx* c, int kclass, const float* W, int M, int K, const float* Xh, const float* Xl,
+                int B, int* S_out, cudaStream_t st) {
+  const int S = pick_splits(c, M, K, B);
+  *S_out = S;
+  for (int n0 = 0; n0 < B; n0 += 256) {
+    const int cols = (B - n0) < 256 ? (B - n0) : 256;
+    const int N = gemm_n_for(cols);
+    const CUtensorMap *tW, *tXh, *tXl;
+    int rc = get_tmap(c, W, M, K, kBM, &tW);
+    if (rc) return rc;
+    rc = get_tmap(c, Xh, c->Bpad, K, N, &tXh);
+    if (rc) return rc;
+    rc = get_tmap(c, Xl, c->Bpad, K, N, &tXl);
+    if (rc) return rc;
+    GemmParams g;
+    g.P = c->P;
+    g.M = M; g.K = K; g.S = S; g.B = B; g.n0 = n0;
+    g.tiles_m = (M + kBM - 1) / kBM;
+    g.kblocks = (K + kBK - 1) / kBK;
+    const int stage = 2 * kTileA + 2 * N * kBK * 4;
+    int stages = (225 * 1024 - 1024) / stage;
+    if (stages > 8) stages = 8;
+    g.stages = stages;
+    const void* fn = N == 32 ? (const void*)gemm_3xtf32_kernel<32>
+                   : N == 64 ? (const void*)gemm_3xtf32_kernel<64>
+                   : N == 128 ? (const void*)gemm_3xtf32_kernel<128>
+                              : (const void*)gemm_3xtf32_kernel<256>;
+    int items = g.tiles_m * S;
+    const int grid = items < c->num_sms ? items : c->num_sms;
+    CUtensorMap a = *tW, b = *tXh, d = *tXl;
+    void* args[] = {&a, &b, &d, &g};
+    rc = launch(c, kclass, fn, dim3(grid), dim3(kGemmThreads), (size_t)stages * stage + 1024, 1, args, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
+  const int D = c->D, F = c->F, hs = c->hs, H = c->H, V = c->V;
+  const size_t kv_seq = (size_t)H * c->steps * hs;
+  const size_t kv_layer = kv_seq * c->Bmax;
+  const int* tokp = c->d_ctl + CTL_HDR;
+  const int* posp = c->d_ctl + CTL_HDR + B;
+  int rc, S = 1;
+
+  auto resid_rms = [&](const float* P, int Sp, const float* emb, const float* rms_w) -> int {
+    BatVecParams v;
+    memset(&v, 0, sizeof v);
+    v.P = P; v.S = Sp; v.B = B; v.M = D;
+    v.tok_emb = emb; v.tokp = tokp; v.x = c->x; v.rms_w = rms_w;
+    v.xh = c->XhD; v.xl = c->XlD; v.D = D;
+    void* args[] = {&v};
+    return launch(c, L2B_K_WO, (const void*)bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
+  };
+
+  rc = resid_rms(nullptr, 0, c->tok_emb, c->rms_att);  // x := embedding; rmsnorm of layer 0
+  if (rc) return rc;
+  const int cs = auto_cluster(c, B);
+  for (int l = 0; l < c->L; ++l) {
+    rc = launch_gemm(c, L2B_K_QKV, c->wqkv + (size_t)l * 3 * D * D, 3 * D, D, c->XhD, c->XlD, B, &S, st);
+    if (rc) return rc;
+    {
+      BatQkvParams q;
+      memset(&q, 0, sizeof q);
+      q.P = c->P; q.S = S; q.B = B; q.D = D; q.hs = hs; q.steps = c->steps;
+      q.posp = posp; q.fcr = c->fcr; q.fci = c->fci; q.q = c->q;
+      q.kc = c->kc + (size_t)l * kv_layer; q.vc = c->vc + (size_t)l * kv_layer;
+      q.kv_seq_stride = (long long)kv_seq;
+      void* args[] = {&q};
+      rc = launch(c, L2B_K_QKV, (const void*)bat_qkv_epi_kernel, dim3((3 * D / 2 + 255) / 256, B), dim3(256), 0,
+                  1, args, st);
+      if (rc) return rc;
+    }
+    {
+      AttnParams a;
+      memset(&a, 0, sizeof a);
+      a.q = c->q;
+      a.kc = c->kc + (size_t)l * kv_layer;
+      a.vc = c->vc + (size_t)l * kv_layer;
+      a.xb = c->xb;
+      a.posp = posp;
+      a.H = H; a.hs = hs; a.steps = c->steps;
+      a.q_stride = D; a.xb_stride = D; a.xb_off = 0;
+      a.tileT = kAttnStageBytes / (hs * 4);
+      a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
+      a.tp_size = 1;
+      a.xh = c->XhD; a.xl = c->XlD;
+      const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
+      void* args[] = {&a};
+      rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B), dim3(kAttnThreads), smem, cs,
+                  args, st);
+      if (rc) return rc;
+    }
+    rc = launch_gemm(c, L2B_K_WO, c->wo + (size_t)l * D * D, D, D, c->XhD, c->XlD, B, &S, st);
+    if (rc) return rc;
+    rc = resid_rms(c->P, S, nullptr, c->rms_ffn + (size_t)l * D);
+    if (rc) return rc;
+    rc = launch_gemm(c, L2B_K_W13, c->w13 + (size_t)l * 2 * F * D, 2 * F, D, c->XhD, c->XlD, B, &S, st);
+    if (rc) return rc;
+    {
+      BatSwigluParams w;
+      memset(&w, 0, sizeof w);
+      w.P = c->P; w.S = S; w.B = B; w.F = F; w.xh = c->XhF; w.xl = c->XlF;
+      void* args[] = {&w};
+      rc = launch(c, L2B_K_W13, (const void*)bat_swiglu_kernel, dim3((F + 255) / 256, B), dim3(256), 0, 1, args,
+                  st);
+      if (rc) return rc;
+    }
+    rc = launch_gemm(c, L2B_K_W2, c->w2 + (size_t)l * D * F, D, F, c->XhF, c->XlF, B, &S, st);
+    if (rc) return rc;
+    rc = resid_rms(c->P, S, nullptr, l + 1 < c->L ? c->rms_att + (size_t)(l + 1) * D : c->rms_final);
+    if (rc) return rc;
+  }
+  rc = launch_gemm(c, L2B_K_CLS, c->wcls, V, D, c->XhD, c->XlD, B, &S, st);
+  if (rc) return rc;
+  {
+    BatLogitsParams g;
+    memset(&g, 0, sizeof g);
+    g.P = c->P; g.S = S; g.B = B; g.V = V; g.logits = c->logits; g.ctl = c->d_ctl;
+    g.next = c->d_dev + 1; g.forced = c->d_forced; g.out_tokens = c->d_out;
+    void* args[] = {&g};
+    rc = launch(c, L2B_K_CLS, (const void*)bat_logits_kernel, dim3(B), dim3(1024), 0, 1, args, st);
+    if (rc) return rc;
+    int* ctl = c->d_ctl;
+    void* args2[] = {&ctl};
+    rc = launch(c, L2B_K_CLS, (const void*)bat_step_kernel, dim3(1), dim3(32), 0, 1, args2, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 // One decode step for B sequences: tokens/positions are read from d_ctl.
 int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
+  if (c->opt.tc_min_batch > 0 && B >= c->opt.tc_min_batch && c->P != nullptr)
+    return enqueue_step_batched(c, B, st);
   const int D = c->D, F = c->F, hs = c->hs, H = c->H;
   const size_t kv_seq = (size_t)H * c->steps * hs;
   const size_t kv_layer = kv_seq * c->Bmax;
@@ -540,6 +734,16 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
   const size_t max_grid = (size_t)c->num_sms * 4;
   TRY(dev_alloc(c, &c->blk_val, max_grid * kMaxNB, true));
   TRY(dev_alloc(c, &c->blk_idx, max_grid * kMaxNB, true));
+  if (max_batch > kMaxNB) {
+    // tensor-core path scratch: activations padded to whole 256-column groups
+    c->Bpad = ((max_batch + 255) / 256) * 256;
+    const size_t Mmax = (size_t)(3 * D > 2 * F ? 3 * D : 2 * F) > sV ? (size_t)(3 * D > 2 * F ? 3 * D : 2 * F) : sV;
+    TRY(dev_alloc(c, &c->XhD, (size_t)c->Bpad * sD + 64, true));
+    TRY(dev_alloc(c, &c->XlD, (size_t)c->Bpad * sD + 64, true));
+    TRY(dev_alloc(c, &c->XhF, (size_t)c->Bpad * sF + 64, true));
+    TRY(dev_alloc(c, &c->XlF, (size_t)c->Bpad * sF + 64, true));
+    TRY(dev_alloc(c, &c->P, (size_t)c->Smax * sB * Mmax, false));
+  }
   TRY(dev_alloc(c, &c->d_forced, (size_t)max_steps * sB, true));
   TRY(dev_alloc(c, &c->d_out, (size_t)max_steps * sB, true));
 #undef TRY
@@ -584,7 +788,7 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   float* fl[] = {c->tok_emb, c->rms_att, c->wqkv, c->wo, c->rms_ffn, c->w13, c->w2, c->rms_final,
                  c->fcr, c->fci, c->shared_cls ? nullptr : c->wcls, c->x, c->xb, c->q, c->hb,
-                 c->logits, c->kc, c->vc, c->blk_val};
+                 c->logits, c->kc, c->vc, c->blk_val, c->XhD, c->XlD, c->XhF, c->XlF, c->P};
   for (float* p : fl)
     if (p) cudaFree(p);
   int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out};
@@ -830,6 +1034,10 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.attn_cluster = v;
   } else if (k == "evict_first") {
     o.evict_first = v < 0 ? -1 : (v != 0);
+  } else if (k == "tc_min_batch") {
+    o.tc_min_batch = v < 0 ? 0 : v;
+  } else if (k == "tc_splits") {
+    o.tc_splits = v < 0 ? 0 : v;
   } else {
     return fail(c, L2B_EINVAL, "unknown option '%s'", key);
   }

@@ -102,3 +102,29 @@ def test_7b_properties_256_tokens(pkg, oracle, seven_b):
     ctx.set_option("graph", 1)
     ctx.set_option("pdl", 1)
     assert np.array_equal(np.array(host), a)
+
+
+def test_7b_batched_tensor_core_path(pkg, oracle, seven_b):
+    """16 independent sequences on the tcgen05 3xTF32 path at full 7B size vs the oracle."""
+    hdr, blob, _ = seven_b
+    B = 16
+    oracle.set_threads(oracle.max_threads())
+    try:
+        with pkg.Context(hdr, device=0, max_batch=B, max_steps=8) as ctx:
+            pkg.synth.upload_blob(ctx, hdr, blob)
+            toks0 = pkg.synth.teacher_tokens(B, 32000, 77)
+            toks1 = pkg.synth.teacher_tokens(B, 32000, 78)
+            lg0, _ = ctx.forward_batch(toks0, np.zeros(B, np.int32))
+            lg1, am1 = ctx.forward_batch(toks1, np.ones(B, np.int32))
+            worst = 0.0
+            for b in range(0, B, 3):
+                ref = oracle.Model(hdr, blob)
+                w0 = ref.forward(int(toks0[b]), 0)
+                w1 = ref.forward(int(toks1[b]), 1)
+                worst = max(worst, float(np.abs(lg0[b] - w0).max()), float(np.abs(lg1[b] - w1).max()))
+                assert np.allclose(lg0[b], w0, rtol=RTOL, atol=ATOL), (b, np.abs(lg0[b] - w0).max())
+                assert np.allclose(lg1[b], w1, rtol=RTOL, atol=ATOL), (b, np.abs(lg1[b] - w1).max())
+                assert am1[b] == oracle.argmax(lg1[b])
+            print("7B batched (B=16, 3xTF32 tcgen05): max|dlogit| %.3g" % worst)
+    finally:
+        oracle.set_threads(1)
