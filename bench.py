@@ -55,6 +55,14 @@ def ncu_traffic(kernel):
     return None
 
 
+def tensor_peak():
+    """Dense TF32 tensor peak in TFLOP/s: half the measured bf16 figure."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["bf16_tflops_sustained"]) / 2.0
+    return 1400.0 / 2.0
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -194,32 +202,34 @@ def cpu_sample(oracle, hdr, blob, threads, budget_s, max_tokens, warm=0):
     return n / dt, n, dt
 
 
-def run_workload(pkg, name, device, steps, warmup, seed, want_profile, keep_host=False):
-    """Returns dict with device-loop and e2e timings for one batch-1 workload on this rank."""
-    import torch
+def run_workload(pkg, name, device, steps, warmup, seed, B=1, keep_host=False):
+    """Builds the named architecture on this rank's GPU (random-init weights generated on the
+    device) with B independent sequences; returns (state, loop_device)."""
     hdr = pkg.synth.header(name)
     S = hdr[6]
     rows = min(S, warmup + steps)
-    ctx = pkg.Context(hdr, device=device, max_batch=1, max_steps=rows)
+    ctx = pkg.Context(hdr, device=device, max_batch=B, max_steps=rows)
     blob = build_weights_on_gpu(pkg, ctx, hdr, seed, "cuda:%d" % device, keep_host)
-    out = {"hdr": hdr, "ctx": ctx, "blob": blob, "rows": rows}
+    out = {"hdr": hdr, "ctx": ctx, "blob": blob, "rows": rows, "B": B}
+    V = abs(hdr[5])
 
     def loop_device(n, pos0, tok0):
-        """n tokens of the device-resident greedy loop, wrapping at the KV capacity."""
-        ms, launches, done, tok, pos = 0.0, 0, 0, tok0, pos0
+        """n steps of the device-resident greedy loop (all B sequences), wrapping at the KV
+        capacity.  Returns (device ms, launches, last tokens, next pos)."""
+        ms, launches, done, tok, pos = 0.0, 0, 0, np.array(tok0, dtype=np.int32), pos0
         while done < n:
             chunk = min(n - done, rows - pos)
-            toks = ctx.generate_greedy([tok], [pos], chunk)
+            toks = ctx.generate_greedy(tok, np.full(B, pos, np.int32), chunk)
             ms += ctx.last_device_ms()
             launches += ctx.last_launches()
-            tok = int(toks[-1, 0])
-            if tok == 1:
-                tok = 2
+            tok = toks[-1].copy()
+            tok[tok == 1] = 2
             done += chunk
             pos = (pos + chunk) % rows
         return ms, launches, tok, pos
 
-    _, _, tok, pos = loop_device(warmup, 0, 1)
+    first = np.ones(B, dtype=np.int32) if B == 1 else pkg.synth.teacher_tokens(B, V, seed + 99)
+    _, _, tok, pos = loop_device(warmup, 0, first)
     out["after_warmup"] = (tok, pos)
     return out, loop_device
 
@@ -231,6 +241,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="llama2-7b")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="GLOBAL number of independent sequences, partitioned over the ranks "
+                         "(strong scaling); 0 = one sequence per GPU (weak scaling, the default)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true")
@@ -246,11 +259,21 @@ def main():
     from oracle import l2ref as oracle  # checker / CPU baseline only
 
     hdr = pkg.synth.header(args.workload)
-    base_cfg = {"workload": "%s architecture, random-init fp32, batch-1 greedy decode (-t 0), "
-                            "%d tokens/rank" % (args.workload, args.steps),
-                "dim": hdr[0], "hidden_dim": hdr[1], "n_layers": hdr[2], "n_heads": hdr[3],
-                "vocab": abs(hdr[5]), "batch_per_gpu": 1,
-                "parallelism": "independent sequences per GPU (weights replicated, no collective)",
+    D, F, L, H = hdr[:4]
+    V = abs(hdr[5])
+    if args.batch > 0:
+        assert args.batch % world == 0, "--batch must be divisible by the number of ranks"
+        B = args.batch // world
+        scaling = "strong"
+        par = "%d independent sequences partitioned over %d GPU(s), %d per GPU (weights replicated, " \
+              "no data-path collective)" % (args.batch, world, B)
+    else:
+        B, scaling = 1, "weak"
+        par = "independent sequences per GPU (weights replicated, no collective)"
+    base_cfg = {"workload": "%s architecture, random-init fp32, %s greedy decode (-t 0), %d steps"
+                            % (args.workload, "batch-1" if B == 1 else "batch-%d/GPU" % B, args.steps),
+                "dim": D, "hidden_dim": F, "n_layers": L, "n_heads": H,
+                "vocab": V, "batch_per_gpu": B, "global_batch": B * world, "parallelism": par,
                 "l2": "inputs larger than L2" if pkg.synth.weight_bytes_per_token(hdr) > 126e6
                       else "weights fit the 126 MB L2 (L2-resident; HBM fraction is nominal)"}
 
@@ -270,14 +293,14 @@ def main():
         tps, n, dt = cpu_sample(oracle, hdr, blob, threads, budget, args.steps, warm=warm)
         line = {"impl": "reference", "metric": "decode tokens/sec", "value": tps, "unit": "tokens/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1000.0 / tps, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1000.0 / tps, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f32 storage, f64 accumulate", "data": "synthetic",
                 "config": base_cfg,
                 "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
                                  "sample": "oracle/l2ref.c (C port of llama2.ts:205-303; no JS runtime "
                                            "in the image), matmul rows split over %d host threads "
-                                           "(bit-identical to 1 thread), %d warm-up + %d timed tokens "
-                                           "from pos %d, %.1f s (time-capped at %.0f s)"
+                                           "(bit-identical to 1 thread), one sequence, %d warm-up + %d "
+                                           "timed tokens from pos %d, %.1f s (time-capped at %.0f s)"
                                            % (threads, warm, n, warm, dt, budget)},
                 "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
@@ -313,100 +336,120 @@ def main():
         want_cpu, cpu_skip = False, "host memory too small for a %.1f GB checkpoint copy" % (
             4e-9 * pkg.synth.weight_floats(hdr))
     st, loop_device = run_workload(pkg, args.workload, local_rank, args.steps, args.warmup,
-                                   args.seed + rank, True, keep_host=want_cpu)
+                                   args.seed + rank, B=B, keep_host=want_cpu)
     ctx, rows = st["ctx"], st["rows"]
     for kv in args.opt:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
     if args.opt:
-        loop_device(args.warmup, 0, 1)
+        loop_device(args.warmup, 0, st["after_warmup"][0])
     tok, pos = st["after_warmup"]
 
     clocks = ClockSampler(local_rank)
     clocks.start()
-    # ---- timed region 1: device-resident loop, K tokens (inputs already in HBM)
+    # ---- timed region 1: device-resident loop, K steps (inputs already in HBM)
     barrier()
     ms, launches, tok2, pos2 = loop_device(args.steps, pos, tok)
     barrier()
     ms = max_over_ranks(ms)
-    # ---- timed region 2: end to end through the C ABI, host buffers, one call per token
-    t_tok, t_pos = tok, pos
+    # ---- timed region 2: end to end through the C ABI, host buffers, one call per step
+    t_tok, t_pos = tok.copy(), pos
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        nxt = ctx.forward_argmax(t_tok, t_pos)
-        t_tok = nxt if nxt != 1 else 2
+        if B == 1:
+            nxt = ctx.forward_argmax(int(t_tok[0]), t_pos)
+            t_tok[0] = nxt if nxt != 1 else 2
+        else:
+            _, am = ctx.forward_batch(t_tok, np.full(B, t_pos, np.int32), want_logits=False)
+            t_tok = np.where(am == 1, 2, am).astype(np.int32)
         t_pos = (t_pos + 1) % rows
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
     e2e_s = max_over_ranks(e2e_s)
     # same, returning the full logits to the host (the temperature / top-p path)
-    lg = np.empty(abs(hdr[5]), dtype=np.float32)
-    n_lg = min(args.steps, 64)
+    n_lg = min(args.steps, 32)
     t0 = time.perf_counter()
     for _ in range(n_lg):
-        ctx.forward(t_tok, t_pos, lg)
-        t_tok = int(np.argmax(lg)) or 2
+        lg, _ = ctx.forward_batch(t_tok, np.full(B, t_pos, np.int32), want_argmax=False)
+        t_tok = np.argmax(lg, axis=1).astype(np.int32)
+        t_tok[t_tok == 1] = 2
         t_pos = (t_pos + 1) % rows
     e2e_logits_s = (time.perf_counter() - t0) * args.steps / n_lg
     clk = clocks.stop()
 
-    # ---- per-kernel CUDA-event times (no graph / PDL overlap), 4 steps mid-sequence
-    kms = np.zeros(pkg.capi.K_COUNT)
-    kn = np.zeros(pkg.capi.K_COUNT)
+    # ---- per-kernel CUDA-event times (no graph / PDL overlap), 3 steps mid-sequence
+    K = pkg.capi
+    kms = np.zeros(K.K_COUNT)
+    kn = np.zeros(K.K_COUNT)
     ppos = min(rows - 5, max(0, args.warmup + args.steps // 2))
     for i in range(4):
-        a, b = ctx.profile_step(2 + i, ppos + i)
+        a, b = ctx.profile_batch(np.full(B, 2 + i, np.int32), np.full(B, ppos + i, np.int32))
         if i > 0:
             kms += a
             kn += b
-    D, F, L, H = hdr[:4]
-    V = abs(hdr[5])
-    kbytes = {pkg.capi.K_QKV: 4 * (3 * D * D + 2 * D + 3 * D),
-              pkg.capi.K_ATTN: 4 * (2 * (ppos + 2) * D + 2 * D),
-              pkg.capi.K_WO: 4 * (D * D + 3 * D),
-              pkg.capi.K_W13: 4 * (2 * F * D + 2 * D + F),
-              pkg.capi.K_W2: 4 * (D * F + F + 2 * D),
-              pkg.capi.K_CLS: 4 * (V * D + 2 * D + V)}
+    kv_b = 4 * (2 * (ppos + 2) * D + 2 * D) * B
+    act = 4 * B
+    kbytes = {K.K_QKV: 4 * 3 * D * D + act * 5 * D, K.K_ATTN: kv_b,
+              K.K_WO: 4 * D * D + act * 3 * D, K.K_W13: 4 * 2 * F * D + act * (2 * D + F),
+              K.K_W2: 4 * D * F + act * (F + 2 * D), K.K_CLS: 4 * V * D + act * (2 * D + V),
+              K.K_GEMM_QKV: 4 * 3 * D * D + act * 5 * D, K.K_GEMM_WO: 4 * D * D + act * 3 * D,
+              K.K_GEMM_W13: 4 * 2 * F * D + act * (2 * D + 2 * F), K.K_GEMM_W2: 4 * D * F + act * (F + D),
+              K.K_GEMM_CLS: 4 * V * D + act * (D + V), K.K_BATCH_EPI: 0}
+    kflops = {K.K_GEMM_QKV: 2.0 * 3 * D * D * B, K.K_GEMM_WO: 2.0 * D * D * B,
+              K.K_GEMM_W13: 2.0 * 2 * F * D * B, K.K_GEMM_W2: 2.0 * D * F * B, K.K_GEMM_CLS: 2.0 * V * D * B}
     peak, peak_src = peaks()
+    tpeak = tensor_peak()
     per_kernel = {}
-    for k in range(pkg.capi.K_COUNT):
+    for k in range(K.K_COUNT):
         if kn[k] > 0:
             avg_ms = kms[k] / kn[k]
-            per_kernel[pkg.capi.KERNEL_NAMES[k]] = {
-                "avg_us": round(1000 * avg_ms, 2), "launches_per_step": int(kn[k] / 3),
-                "bytes": kbytes[k], "gbs": round(kbytes[k] / (avg_ms * 1e-3) / 1e9, 1)}
-    dom = max(range(pkg.capi.K_COUNT), key=lambda k: kms[k])
+            d = {"avg_us": round(1000 * avg_ms, 2), "launches_per_step": int(kn[k] / 3),
+                 "share_of_step": round(float(kms[k] / kms.sum()), 4)}
+            if kbytes.get(k):
+                d["bytes"] = kbytes[k]
+                d["gbs"] = round(kbytes[k] / (avg_ms * 1e-3) / 1e9, 1)
+            if k in kflops:
+                d["tflops_3xtf32"] = round(3 * kflops[k] / (avg_ms * 1e-3) / 1e12, 1)
+            per_kernel[K.KERNEL_NAMES[k]] = d
+    dom = max((k for k in range(K.K_COUNT) if k != K.K_BATCH_EPI), key=lambda k: kms[k])
     dom_ms = kms[dom] / kn[dom]
-    achieved = kbytes[dom] / (dom_ms * 1e-3) / 1e9
+    hbm_rate = kbytes[dom] / (dom_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": K.KERNEL_NAMES[dom], "achieved": hbm_rate, "peak": peak,
+            "unit": "GB/s", "frac": hbm_rate / peak, "peak_source": peak_src,
+            "traffic": ncu_traffic(K.KERNEL_NAMES[dom]) if (args.workload == "llama2-7b" and B == 1) else None,
+            "algorithmic_bytes_per_launch": kbytes[dom], "avg_launch_us": 1000 * dom_ms}
+    if dom in kflops:
+        tf = 3 * kflops[dom] / (dom_ms * 1e-3) / 1e12
+        roof["tensor"] = {"achieved": tf, "peak": tpeak, "unit": "TFLOP/s (3xTF32 issued)", "frac": tf / tpeak,
+                          "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)"}
+        if tf / tpeak > hbm_rate / peak:
+            roof.update({"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak})
 
-    n_tok = args.steps * world
+    n_tok = args.steps * world * B
     value = n_tok / (ms * 1e-3)
     mean_pos = (pos + (args.steps - 1) / 2.0) % rows
-    sbytes = pkg.synth.step_bytes(hdr, mean_pos)
+    sbytes = pkg.synth.step_bytes(hdr, mean_pos, B=B)
+    step_s = ms / args.steps * 1e-3
+    roof["step"] = {"bytes_per_step": sbytes, "achieved": sbytes / step_s / 1e9,
+                    "frac": sbytes / step_s / 1e9 / peak,
+                    "roofline_tokens_per_s_per_gpu": B * peak * 1e9 / sbytes}
+    roof["per_kernel"] = per_kernel
     line = {
         "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 storage, f64 accumulate" if True else "f32", "data": "synthetic",
-        "config": base_cfg,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32 storage, f64 accumulate" if B < 9 else "f32 storage, 3xTF32 tensor-core products, f32 accumulate",
+        "data": "synthetic", "config": base_cfg,
         "e2e": {"value": n_tok / e2e_s, "unit": "tokens/s",
-                "h2d_bytes_per_step": 4 * (4 + 2), "d2h_bytes_per_step": 4,
-                "call": "l2b_forward_argmax(token,pos) per token (-t 0)",
-                "logits_variant_tokens_per_s": world * args.steps / e2e_logits_s,
-                "logits_variant_d2h_bytes_per_step": 4 * V},
+                "h2d_bytes_per_step": 4 * (4 + 2 * B), "d2h_bytes_per_step": 4 * B,
+                "call": "l2b_forward_argmax(token,pos) per token (-t 0)" if B == 1 else
+                        "l2b_forward_batch(B,tokens,pos,NULL,argmax) per step (-t 0)",
+                "logits_variant_tokens_per_s": n_tok / e2e_logits_s,
+                "logits_variant_d2h_bytes_per_step": 4 * V * B},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": pkg.capi.KERNEL_NAMES[dom],
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src,
-                     "traffic": ncu_traffic(pkg.capi.KERNEL_NAMES[dom]) if args.workload == "llama2-7b" else None,
-                     "algorithmic_bytes_per_launch": kbytes[dom],
-                     "avg_launch_us": 1000 * dom_ms,
-                     "step": {"bytes_per_token": sbytes, "achieved": sbytes / (ms / args.steps * 1e-3) / 1e9,
-                              "frac": sbytes / (ms / args.steps * 1e-3) / 1e9 / peak,
-                              "roofline_tokens_per_s_per_gpu": peak * 1e9 / sbytes},
-                     "per_kernel": per_kernel},
+        "roofline": roof,
         "clocks": clk,
     }
 
@@ -415,7 +458,8 @@ def main():
         tps, n, dt = cpu_sample(oracle, hdr, st["blob"], 1, 20.0, 4)
         # parity spot-check of the very workload being timed (first token, full size)
         ctx.reset()
-        got = ctx.forward(1, 0)
+        t0s = np.ones(B, dtype=np.int32)
+        got, _ = ctx.forward_batch(t0s, np.zeros(B, np.int32), want_argmax=False)
         want = oracle.Model(hdr, st["blob"])
         oracle.set_threads(oracle.max_threads())
         ref = want.forward(1, 0)
@@ -423,15 +467,15 @@ def main():
         line["cpu_baseline"] = {
             "value": tps, "unit": "tokens/s", "cores": 1, "kind": "port",
             "sample": "oracle/l2ref.c (C port of the reference forward; the reference is one JS "
-                      "thread and no JS runtime exists in the image), first %d tokens of this "
-                      "workload, %.1f s" % (n, dt),
-            "parity_vs_gpu_max_abs_logit_diff": float(np.max(np.abs(got - ref))),
-            "parity_bit_identical_frac": float(np.mean(got == ref))}
+                      "thread and no JS runtime exists in the image), first %d tokens of one "
+                      "sequence of this workload, %.1f s" % (n, dt),
+            "parity_vs_gpu_max_abs_logit_diff": float(np.max(np.abs(got - ref[None, :]))),
+            "parity_bit_identical_frac": float(np.mean(got == ref[None, :]))}
     elif rank == 0:
         line["cpu_baseline"] = {"value": None, "skipped": cpu_skip or "N > 1 or --no-cpu-baseline"}
     ctx.close()
 
-    if rank == 0 and world == 1 and not args.no_others:
+    if rank == 0 and world == 1 and B == 1 and not args.no_others:
         others = {}
         for name in ("stories15M", "stories42M", "stories110M"):
             if name == args.workload:
@@ -439,7 +483,7 @@ def main():
             try:
                 h2 = pkg.synth.header(name)
                 k2 = min(args.steps, h2[6] - args.warmup)
-                st2, loop2 = run_workload(pkg, name, local_rank, k2, args.warmup, args.seed, False)
+                st2, loop2 = run_workload(pkg, name, local_rank, k2, args.warmup, args.seed)
                 t2, p2 = st2["after_warmup"]
                 torch.cuda.synchronize()
                 ms2, _, _, _ = loop2(k2, p2, t2)

@@ -129,7 +129,15 @@ int64_t l2b_last_launches(const l2b_ctx* ctx);
 #define L2B_K_W13   3   /* rmsnorm -> w1/w3 matvec -> SwiGLU              llama2.ts:276-289 */
 #define L2B_K_W2    4   /* w2 matvec + residual                           llama2.ts:292-295 */
 #define L2B_K_CLS   5   /* final rmsnorm -> wcls matvec -> argmax         llama2.ts:299-302 */
-#define L2B_K_COUNT 6
+/* batched tensor-core path (B >= tc_min_batch): the same five matmuls as tcgen05 GEMMs   */
+#define L2B_K_GEMM_QKV 6
+#define L2B_K_GEMM_WO  7
+#define L2B_K_GEMM_W13 8
+#define L2B_K_GEMM_W2  9
+#define L2B_K_GEMM_CLS 10
+#define L2B_K_BATCH_EPI 11 /* fused elementwise kernels between the GEMMs (RoPE+KV write,
+                              residual+rmsnorm, SwiGLU, logits+argmax)                    */
+#define L2B_K_COUNT 12
 
 /* One batch-1 decode step run WITHOUT graph/PDL overlap and with a CUDA event
  * between every two launches: ms_per_class[k] / launches_per_class[k]
@@ -138,6 +146,9 @@ int64_t l2b_last_launches(const l2b_ctx* ctx);
  * state effects as l2b_forward.                                                */
 int l2b_profile_step(l2b_ctx* ctx, int32_t token, int32_t pos, float* ms_per_class,
                      int32_t* launches_per_class);
+/* Same for one step of B sequences (l2b_forward_batch semantics).                        */
+int l2b_profile_batch(l2b_ctx* ctx, int32_t B, const int32_t* tokens, const int32_t* pos,
+                      float* ms_per_class, int32_t* launches_per_class);
 
 /* Debug/parity taps: copy device RunState buffers (llama2.ts:131-163) of
  * sequence `seq` to host.  Key/value rows come back in the reference's row

@@ -25,9 +25,10 @@ LAYERED = {T_RMS_ATT_WEIGHT, T_WQ, T_WK, T_WV, T_WO, T_RMS_FFN_WEIGHT, T_W1, T_W
 # error codes
 OK, EINVAL, EORDER, ECUDA, ESTATE, ENOMEM, ECOMM = 0, -1, -2, -3, -4, -5, -6
 # kernel classes / state taps
-K_QKV, K_ATTN, K_WO, K_W13, K_W2, K_CLS, K_COUNT = 0, 1, 2, 3, 4, 5, 6
+K_QKV, K_ATTN, K_WO, K_W13, K_W2, K_CLS = 0, 1, 2, 3, 4, 5
+K_GEMM_QKV, K_GEMM_WO, K_GEMM_W13, K_GEMM_W2, K_GEMM_CLS, K_BATCH_EPI, K_COUNT = 6, 7, 8, 9, 10, 11, 12
 KERNEL_NAMES = ["qkv_rope_kvwrite", "attention", "wo_residual", "w13_swiglu", "w2_residual",
-                "cls_argmax"]
+                "cls_argmax", "gemm_qkv", "gemm_wo", "gemm_w13", "gemm_w2", "gemm_cls", "batch_epilogues"]
 S_X, S_KEY_ROW, S_VALUE_ROW, S_Q, S_XB, S_HB, S_LOGITS = range(7)
 
 
@@ -58,6 +59,7 @@ _SIGNATURES = {
     "l2b_last_device_ms": (_f32, [_p]),
     "l2b_last_launches": (_i64, [_p]),
     "l2b_profile_step": (C.c_int, [_p, _i32, _i32, _p, _p]),
+    "l2b_profile_batch": (C.c_int, [_p, _i32, _p, _p, _p, _p]),
     "l2b_read_state": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _u64]),
     "l2b_reset": (C.c_int, [_p]),
     "l2b_set_option": (C.c_int, [_p, C.c_char_p, _i64]),
@@ -218,6 +220,15 @@ class Context:
         ms = np.zeros(K_COUNT, dtype=np.float32)
         n = np.zeros(K_COUNT, dtype=np.int32)
         self._check(self.lib.dll.l2b_profile_step(self._h, token, pos, _ptr(ms), _ptr(n)))
+        return ms, n
+
+    def profile_batch(self, tokens, pos):
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        ms = np.zeros(K_COUNT, dtype=np.float32)
+        n = np.zeros(K_COUNT, dtype=np.int32)
+        self._check(self.lib.dll.l2b_profile_batch(self._h, tokens.size, _ptr(tokens), _ptr(pos),
+                                                   _ptr(ms), _ptr(n)))
         return ms, n
 
     def read_state(self, which, seq=0, layer=0, pos=0):

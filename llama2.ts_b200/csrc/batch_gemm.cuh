@@ -12,20 +12,29 @@
 // The tensor core adds into its fp32 accumulator with truncation, a bias of ~half an ulp
 // per tcgen05.mma that grows with the length of the accumulation chain (measured: logits
 // error proportional to K per split).  Chains are kept short three ways: the two small
-// terms go to their own accumulator (its truncation error is 2^-11 smaller), the w_hi*x_hi
-// terms rotate over G "main" accumulators (TMEM has 512 columns: G = 7 for N <= 64, 3 for
-// N = 128, 1 for N = 256), and k is split over work items; all partial accumulators are
-// added with round-to-nearest fp32 in the epilogues.
+// terms go to their own accumulator (its truncation error is 2^-11 smaller), the
+// accumulators rotate over G copies in TMEM (512 columns: G = 4 for N = 32, 2 for N = 64, 1
+// above), and k is split over work items; all partial accumulators are added with
+// round-to-nearest fp32 in the epilogues.
+//
+// For N <= 128 the two products that share the operand w_hi are issued as ONE MMA of width
+// 2N against the stacked activation tile [x_hi ; x_lo] (they are adjacent in shared memory),
+// landing in adjacent accumulators (main | small); w_lo*x_hi is a second MMA of width N into
+// the small one.  At small N the MMA is bound by its shared-memory operand reads, and this
+// reads the 4 KB weight operand twice instead of three times per K=8 step.
 // Weights arrive ONCE from HBM as fp32 through TMA (SWIZZLE_128B tiles); four
 // "splitter" warps derive the hi/lo tiles in shared memory in place (an elementwise
 // rewrite, so the swizzled layout is preserved), the activations are pre-split by
 // the epilogue kernel that produced them.
 //
-// Warp roles of the 256-thread CTA (one CTA per SM, persistent over work items):
-//   warp 0      TMA producer   (cp.async.bulk.tensor, ring of `stages` stages)
+// Warp roles of the 384-thread CTA (one CTA per SM, persistent over work items):
+//   warp 0      TMA producer   (cp.async.bulk.tensor into the deep landing ring)
 //   warp 1      MMA issuer     (one elected lane, 12 x tcgen05.mma per 32-float k-block)
 //   warp 2      TMEM allocator
-//   warps 4-7   splitter, then epilogue (tcgen05.ld -> partial sums in global memory)
+//   warps 4-7   splitter       (hi/lo tiles of the weights)
+//   warps 8-11  epilogue       (tcgen05.ld -> partial sums in global memory); for N <= 128
+//               the accumulators are double-buffered in TMEM so the next item's MMAs run
+//               while this one drains
 // A work item is (128-row tile of W, k-split); partial sums go to P[split][b][m] and
 // are reduced in a fixed order by the fused elementwise kernels at the end of this
 // file (RoPE + KV write, residual + rmsnorm, SwiGLU, logits + argmax), which also
@@ -39,7 +48,7 @@
 
 namespace l2b {
 
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
 constexpr int kBM = 128;                    // weight rows per tile (UMMA M)
 constexpr int kBK = 32;                     // floats per k-block: one 128-byte swizzle row
 constexpr int kTileA = kBM * kBK * 4;       // 16 KB
@@ -56,7 +65,10 @@ struct GemmParams {
   int n0;         // first column of this launch (batches > 256 run in column groups)
   int tiles_m;    // ceil(M / 128)
   int kblocks;    // ceil(K / 32)
-  int stages;
+  int dl;         // landing-ring depth (raw weight tiles in flight)
+  int dop;        // operand-ring depth
+  int rewrite_hi; // 1: weights' hi part rounded to nearest and rewritten in shared memory;
+                  // 0: hi = hardware truncation of the raw tile (saves 16 KB of st.shared per k-block)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1,
@@ -104,37 +116,73 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Ring helper: slot index + phase parity of a circular buffer of `depth` slots.
+struct Ring {
+  int i, ph, depth;
+  __device__ __forceinline__ Ring(int d) : i(0), ph(0), depth(d) {}
+  __device__ __forceinline__ void next() {
+    if (++i == depth) { i = 0; ph ^= 1; }
+  }
+};
+
 // N = padded number of sequences handled by one MMA (UMMA N): 32, 64, 128 or 256
+//
+// Shared memory holds two rings.  The LANDING ring (p.dl slots) receives everything TMA
+// brings -- the raw fp32 weight tile (16 KB) and the pre-split (hi, lo) activation tiles of
+// the same k-block -- and is deep, so that many tiles are in flight in HBM / L2 at once; the
+// splitter turns a landed weight tile into its TF32-exact hi part IN PLACE.  The OPERAND
+// ring (p.dop slots of 16 KB) holds the only thing that is produced on the SM: the lo part
+// of the weight tile.  Only the short split -> MMA -> commit chain is serialised per
+// operand slot; the long HBM latency is covered by the landing ring.
 template <int N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXh,
                    const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ GemmParams p) {
   constexpr int kTileX = N * kBK * 4;
-  constexpr int kStage = 2 * kTileA + 2 * kTileX;
-  constexpr int kMaxStages = 8;
+  // N <= 128: the activation tiles travel with the weight tile in the landing ring (deep
+  // prefetch of everything; HBM/L2-latency regime).  N = 256 is tensor-bound and its 64 KB of
+  // activation tiles per k-block would leave room for only two landing slots, so there they
+  // live in the (2-deep) operand ring and have their own producer thread (warp 3).
+  constexpr bool kXInLanding = N <= 128;
+  constexpr int kLandSlot = kTileA + (kXInLanding ? 2 * kTileX : 0);   // A (raw -> hi) [| X_hi | X_lo]
+  constexpr int kOpSlot = kTileA + (kXInLanding ? 0 : 2 * kTileX);     // A_lo [| X_hi | X_lo]
+  constexpr int kMaxDepth = 12;
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
-  constexpr int G = N == 256 ? 1 : (N == 128 ? 3 : 7);           // main accumulators
-  constexpr uint32_t kTmemCols = (G + 1) * N <= 256 ? 256u : 512u;  // power of two >= (G+1)*N
+  constexpr bool kWide = N <= 128;                     // stacked [x_hi ; x_lo] MMA of width 2N
+  constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | (8u << 24);
+  constexpr int G = N == 32 ? 4 : (N == 64 ? 2 : 1);   // (main | small) accumulator pairs per set
+  constexpr int kSetCols = G * 2 * N;                  // 256 (N <= 128) or 512 (N = 256)
+  constexpr int kSets = 512 / kSetCols;                // accumulator sets: 2, or 1 for N = 256
+  constexpr uint32_t kTmemCols = 512u;
 
   extern __shared__ __align__(1024) unsigned char gsm[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages], split_bar[kMaxStages], empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar, tmem_empty_bar;
+  __shared__ __align__(8) uint64_t land_full[kMaxDepth], land_empty[kMaxDepth];
+  __shared__ __align__(8) uint64_t op_empty[4], split_done[4], op_xfull[4];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
   griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stages = p.stages;
+  const int DL = p.dl, DO = p.dop;
   // dynamic shared memory is only guaranteed 16-byte aligned: round up to the swizzle atom
   unsigned char* sm = gsm + ((1024u - (smem_u32(gsm) & 1023u)) & 1023u);
+  unsigned char* land = sm;                             // DL x kLandSlot
+  unsigned char* ops = sm + (size_t)DL * kLandSlot;     // DO x kOpSlot
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 4);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < DL; ++s) {
+      mbar_init(&land_full[s], 1);
+      mbar_init(&land_empty[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
-    mbar_init(&tmem_empty_bar, 4);
+    for (int s = 0; s < DO; ++s) {
+      mbar_init(&op_empty[s], 1);
+      mbar_init(&op_xfull[s], 1);
+      mbar_init(&split_done[s], 4);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
     mbar_fence_init();
     tmap_prefetch(&tmW);
     tmap_prefetch(&tmXh);
@@ -151,118 +199,214 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  griddep_wait();  // the activations X were written by the previous kernel
-
   const int n_items = p.tiles_m * p.S;
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
+    // Weights never depend on the previous kernel: the first DL weight tiles are requested
+    // BEFORE griddep_wait(), their activation tiles right after it (same mbarrier, the
+    // expected byte count covers both).
     if (lane == 0) {
-      int st = 0, ph = 0;
+      struct Seq {  // the (tile, k-block) sequence of this CTA
+        int it, kb, kb1, mt;
+        const GemmParams& p;
+        int n_items, stride;
+        __device__ Seq(const GemmParams& p_, int first, int n, int st) : p(p_), n_items(n), stride(st) {
+          it = first;
+          load();
+        }
+        __device__ void load() {
+          if (it < n_items) {
+            const int split = it / p.tiles_m;
+            mt = it - split * p.tiles_m;
+            kb = (int)(((long long)p.kblocks * split) / p.S);
+            kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
+          }
+        }
+        __device__ bool done() const { return it >= n_items; }
+        __device__ void next() {
+          if (++kb >= kb1) {
+            it += stride;
+            load();
+          }
+        }
+      };
+      Seq a(p, blockIdx.x, n_items, gridDim.x), x(p, blockIdx.x, n_items, gridDim.x);
+      Ring ra(DL), rx(DL);
+      int ahead = 0;
+      while (!a.done() && ahead < DL) {  // prologue: weights only
+        mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
+        tma_load_2d(land + (size_t)ra.i * kLandSlot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
+        ra.next();
+        a.next();
+        ++ahead;
+      }
+      if (kXInLanding) {
+        griddep_wait();  // X was written by the previous kernel
+        for (int j = 0; j < ahead; ++j) {
+          unsigned char* slot = land + (size_t)rx.i * kLandSlot;
+          tma_load_2d(slot + kTileA, &tmXh, x.kb * kBK, p.n0, &land_full[rx.i]);
+          tma_load_2d(slot + kTileA + kTileX, &tmXl, x.kb * kBK, p.n0, &land_full[rx.i]);
+          rx.next();
+          x.next();
+        }
+      }
+      while (!a.done()) {  // steady state
+        mbar_wait(&land_empty[ra.i], ra.ph ^ 1);
+        unsigned char* slot = land + (size_t)ra.i * kLandSlot;
+        mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
+        tma_load_2d(slot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
+        if (kXInLanding) {
+          tma_load_2d(slot + kTileA, &tmXh, a.kb * kBK, p.n0, &land_full[ra.i]);
+          tma_load_2d(slot + kTileA + kTileX, &tmXl, a.kb * kBK, p.n0, &land_full[ra.i]);
+        }
+        ra.next();
+        a.next();
+      }
+    }
+  } else if (warp == 3 && !kXInLanding) {
+    // ---------------- activation producer (N = 256) ----------------
+    if (lane == 0) {
+      griddep_wait();  // X was written by the previous kernel
+      Ring ro(DO);
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int split = it / p.tiles_m, mt = it - split * p.tiles_m;
+        const int split = it / p.tiles_m;
         const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
         const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[st], ph ^ 1);
-          unsigned char* base = sm + (size_t)st * kStage;
-          mbar_arrive_expect_tx(&full_bar[st], kTileA + 2 * kTileX);
-          tma_load_2d(base, &tmW, kb * kBK, mt * kBM, &full_bar[st]);
-          tma_load_2d(base + 2 * kTileA, &tmXh, kb * kBK, p.n0, &full_bar[st]);
-          tma_load_2d(base + 2 * kTileA + kTileX, &tmXl, kb * kBK, p.n0, &full_bar[st]);
-          if (++st == stages) { st = 0; ph ^= 1; }
+          mbar_wait(&op_empty[ro.i], ro.ph ^ 1);
+          unsigned char* slot = ops + (size_t)ro.i * kOpSlot;
+          mbar_arrive_expect_tx(&op_xfull[ro.i], 2 * kTileX);
+          tma_load_2d(slot + kTileA, &tmXh, kb * kBK, p.n0, &op_xfull[ro.i]);
+          tma_load_2d(slot + kTileA + kTileX, &tmXl, kb * kBK, p.n0, &op_xfull[ro.i]);
+          ro.next();
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      int st = 0, ph = 0, li = 0;
+      Ring rl(DL), ro(DO);
+      int li = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
         const int split = it / p.tiles_m;
         const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
         const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
-        mbar_wait(&tmem_empty_bar, (li & 1) ^ 1);  // epilogue drained the accumulator
+        const int set = li % kSets;
+        mbar_wait(&tmem_empty_bar[set], ((li / kSets) & 1) ^ 1);  // epilogue drained this set
         tc_fence_after();
+        const uint32_t tset = tmem_base + (uint32_t)(set * kSetCols);
         for (int kb = kb0; kb < kb1; ++kb) {
           const int kk = kb - kb0;
-          const uint32_t d_small = tmem_base;                                  // columns [0, N)
-          const uint32_t d_main = tmem_base + (uint32_t)((1 + kk % G) * N);    // rotating main accumulator
-          const uint32_t acc_main = kk >= G ? 1u : 0u;
-          mbar_wait(&split_bar[st], ph);
+          const uint32_t d_main = tset + (uint32_t)((kk % G) * 2 * N);     // rotating pair: main | small
+          const uint32_t d_small = d_main + (uint32_t)N;
+          const uint32_t acc0 = kk >= G ? 1u : 0u;                         // first use overwrites
+          mbar_wait(&split_done[ro.i], ro.ph);   // hi (landing slot) and lo (operand slot) written
+          if (!kXInLanding) mbar_wait(&op_xfull[ro.i], ro.ph);
           tc_fence_after();
-          unsigned char* base = sm + (size_t)st * kStage;
-          const uint64_t dAh = umma_desc_sw128(base), dAl = umma_desc_sw128(base + kTileA);
-          const uint64_t dXh = umma_desc_sw128(base + 2 * kTileA);
-          const uint64_t dXl = umma_desc_sw128(base + 2 * kTileA + kTileX);
+          unsigned char* ls = land + (size_t)rl.i * kLandSlot;
+          unsigned char* os = ops + (size_t)ro.i * kOpSlot;
+          unsigned char* xs = kXInLanding ? ls + kTileA : os + kTileA;
+          const uint64_t dAh = umma_desc_sw128(ls), dAl = umma_desc_sw128(os);
+          const uint64_t dXh = umma_desc_sw128(xs);
+          const uint64_t dXl = umma_desc_sw128(xs + kTileX);
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 step
-            tc_mma_tf32(d_small, dAl + adv, dXh + adv, kIdesc, (kk | k) != 0 ? 1u : 0u);
-            tc_mma_tf32(d_small, dAh + adv, dXl + adv, kIdesc, 1u);
-            tc_mma_tf32(d_main, dAh + adv, dXh + adv, kIdesc, k != 0 ? 1u : acc_main);
+            const uint32_t acc = k != 0 ? 1u : acc0;
+            if (kWide) {
+              tc_mma_tf32(d_main, dAh + adv, dXh + adv, kIdesc2, acc);   // w_hi * [x_hi ; x_lo]
+              tc_mma_tf32(d_small, dAl + adv, dXh + adv, kIdesc, 1u);    // w_lo * x_hi
+            } else {
+              tc_mma_tf32(d_small, dAl + adv, dXh + adv, kIdesc, acc);
+              tc_mma_tf32(d_small, dAh + adv, dXl + adv, kIdesc, 1u);
+              tc_mma_tf32(d_main, dAh + adv, dXh + adv, kIdesc, acc);
+            }
           }
-          tc_commit(&empty_bar[st]);  // frees the stage when these MMAs have read it
-          if (++st == stages) { st = 0; ph ^= 1; }
+          tc_commit(&land_empty[rl.i]);  // both slots are free once these MMAs have read them
+          tc_commit(&op_empty[ro.i]);
+          rl.next();
+          ro.next();
         }
-        tc_commit(&tmem_full_bar);  // accumulator complete
+        tc_commit(&tmem_full_bar[set]);  // accumulators complete
       }
     }
-  } else if (warp >= 4) {
-    // ---------------- splitter + epilogue ----------------
+  } else if (warp >= 4 && warp < 8) {
+    // ---------------- splitter ----------------
     const int t = threadIdx.x - 128;  // 0..127
-    const int wq = warp & 3;          // TMEM lane quadrant this warp may read
-    int st = 0, ph = 0, li = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
-      const int split = it / p.tiles_m, mt = it - split * p.tiles_m;
+    const bool rewrite_hi = p.rewrite_hi != 0;
+    Ring rl(DL), ro(DO);
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int split = it / p.tiles_m;
       const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
       const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[st], ph);
-        uint4* ah = reinterpret_cast<uint4*>(sm + (size_t)st * kStage);
-        uint4* al = reinterpret_cast<uint4*>(sm + (size_t)st * kStage + kTileA);
+        mbar_wait(&op_empty[ro.i], ro.ph ^ 1);  // the lo slot is free again
+        mbar_wait(&land_full[rl.i], rl.ph);     // the raw tile has landed
+        uint4* ah = reinterpret_cast<uint4*>(land + (size_t)rl.i * kLandSlot);
+        uint4* al = reinterpret_cast<uint4*>(ops + (size_t)ro.i * kOpSlot);
 #pragma unroll
         for (int i = 0; i < kTileA / 16 / 128; ++i) {
           const int c = t + i * 128;
           const uint4 v = ah[c];
           uint4 h, l;
-          h.x = tf32_hi_bits(v.x); h.y = tf32_hi_bits(v.y); h.z = tf32_hi_bits(v.z); h.w = tf32_hi_bits(v.w);
+          if (rewrite_hi) {  // round-to-nearest hi, written back in place
+            h.x = tf32_hi_bits(v.x); h.y = tf32_hi_bits(v.y); h.z = tf32_hi_bits(v.z); h.w = tf32_hi_bits(v.w);
+          } else {           // the tensor core ignores the low 13 bits: hi = truncation, tile untouched
+            h.x = v.x & kHiMask; h.y = v.y & kHiMask; h.z = v.z & kHiMask; h.w = v.w & kHiMask;
+          }
           l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
           l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
           l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
           l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-          ah[c] = h;
+          if (rewrite_hi) ah[c] = h;
           al[c] = l;
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to tcgen05.mma
         __syncwarp();
-        if (lane == 0) mbar_arrive(&split_bar[st]);
-        if (++st == stages) { st = 0; ph ^= 1; }
+        if (lane == 0) mbar_arrive(&split_done[ro.i]);
+        rl.next();
+        ro.next();
       }
-      // epilogue: TMEM -> registers -> P[split][b][m]
-      mbar_wait(&tmem_full_bar, li & 1);
+    }
+  } else if (warp >= 8) {
+    // ---------------- epilogue: TMEM -> registers -> P[split][b][m] ----------------
+    const int wq = warp & 3;  // TMEM lane quadrant this warp may read
+    int li = 0;
+    griddep_wait();  // P may still be read by the previous kernel
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+      const int split = it / p.tiles_m, mt = it - split * p.tiles_m;
+      const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
+      const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
+      const int set = li % kSets;
+      mbar_wait(&tmem_full_bar[set], (li / kSets) & 1);
       tc_fence_after();
       const int m = mt * kBM + wq * 32 + lane;
       float* out = p.P + ((size_t)split * p.B + p.n0) * p.M + m;
       const int used = (kb1 - kb0) < G ? (kb1 - kb0) : G;  // main accumulators written by this item
-      const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+      const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * kSetCols);
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += 32) {
         if (p.n0 + c0 >= p.B) break;
         uint32_t r[32];
-        float sum[32];
-        tmem_ld32(lane_base + (uint32_t)(N + c0), r);  // main accumulator 0
+        float sum[32], small[32];
+        tmem_ld32(lane_base + (uint32_t)c0, r);        // pair 0: main
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
+        tmem_ld32(lane_base + (uint32_t)(N + c0), r);  // pair 0: small
+#pragma unroll
+        for (int j = 0; j < 32; ++j) small[j] = __uint_as_float(r[j]);
 #pragma unroll 1
         for (int g = 1; g < used; ++g) {
-          tmem_ld32(lane_base + (uint32_t)((1 + g) * N + c0), r);
+          tmem_ld32(lane_base + (uint32_t)(g * 2 * N + c0), r);
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
-        }
-        tmem_ld32(lane_base + (uint32_t)c0, r);  // small terms last
+          tmem_ld32(lane_base + (uint32_t)(g * 2 * N + N + c0), r);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) small[j] += __uint_as_float(r[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[j] += small[j];
         if (m < p.M) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -271,7 +415,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar);
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[set]);
     }
   }
 

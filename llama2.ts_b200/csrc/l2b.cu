@@ -37,8 +37,9 @@ struct Options {
   int ctas_per_sm = 1;
   int attn_cluster = 0;  // 0 = auto
   int evict_first = -1;  // -1 = auto (weights > L2)
-  int tc_min_batch = 9;  // batches >= this run the tcgen05 GEMM path (0 = never)
+  int tc_min_batch = 5;  // batches >= this run the tcgen05 GEMM path (0 = never)
   int tc_splits = 0;     // 0 = auto k-split per GEMM
+  int tc_rewrite_hi = 0; // see GemmParams::rewrite_hi
 };
 
 }  // namespace
@@ -66,7 +67,7 @@ struct l2b_ctx {
   int *d_forced = nullptr, *d_out = nullptr;
   // batched tensor-core path: pre-split activations [256*groups][D or F], partial sums
   float *XhD = nullptr, *XlD = nullptr, *XhF = nullptr, *XlF = nullptr, *P = nullptr;
-  int Bpad = 0, Smax = 4;
+  int Bpad = 0, Smax = 8;
   std::map<std::pair<const void*, int>, CUtensorMap> tmaps;  // key: (operand base, box rows)
   // host staging (pinned)
   int* h_ctl = nullptr;
@@ -292,7 +293,9 @@ int pick_splits(const l2b_ctx* c, int M, int K, int B) {
     const int items = tiles * s;
     const int waves = (items + c->num_sms - 1) / c->num_sms;
     const double eff = (double)items / ((double)waves * c->num_sms);
-    const double bytes = (double)M * K * 4 / eff + (s > 1 ? 2.0 : 1.0) * s * (double)M * B * 4;
+    // weight stream at the achieved wave efficiency + partial-sum write/read + ~1 us of
+    // pipeline restart per item round, all in "bytes at HBM speed"
+    const double bytes = (double)M * K * 4 / eff + 2.0 * s * (double)M * B * 4 + waves * 6.0e6;
     if (bytes < best) { best = bytes; best_s = s; }
   }
   return best_s;
@@ -317,10 +320,13 @@ int launch_gemm(l2b_ctx* c, int kclass, const float* W, int M, int K, const floa
     g.M = M; g.K = K; g.S = S; g.B = B; g.n0 = n0;
     g.tiles_m = (M + kBM - 1) / kBM;
     g.kblocks = (K + kBK - 1) / kBK;
-    const int stage = 2 * kTileA + 2 * N * kBK * 4;
-    int stages = (225 * 1024 - 1024) / stage;
-    if (stages > 8) stages = 8;
-    g.stages = stages;
+    // operand ring (weight lo tiles): 3 slots; the rest of shared memory is landing ring
+    const int xbytes = 2 * N * kBK * 4;
+    const int op_slot = kTileA + (N <= 128 ? 0 : xbytes), land_slot = kTileA + (N <= 128 ? xbytes : 0);
+    g.dop = N <= 128 ? 3 : 2;
+    g.rewrite_hi = c->opt.tc_rewrite_hi;
+    g.dl = (224 * 1024 - g.dop * op_slot) / land_slot;
+    if (g.dl > 12) g.dl = 12;
     const void* fn = N == 32 ? (const void*)gemm_3xtf32_kernel<32>
                    : N == 64 ? (const void*)gemm_3xtf32_kernel<64>
                    : N == 128 ? (const void*)gemm_3xtf32_kernel<128>
@@ -329,7 +335,7 @@ int launch_gemm(l2b_ctx* c, int kclass, const float* W, int M, int K, const floa
     const int grid = items < c->num_sms ? items : c->num_sms;
     CUtensorMap a = *tW, b = *tXh, d = *tXl;
     void* args[] = {&a, &b, &d, &g};
-    rc = launch(c, kclass, fn, dim3(grid), dim3(kGemmThreads), (size_t)stages * stage + 1024, 1, args, st);
+    rc = launch(c, kclass, fn, dim3(grid), dim3(kGemmThreads), (size_t)g.dl * land_slot + (size_t)g.dop * op_slot + 1024, 1, args, st);
     if (rc) return rc;
   }
   return 0;
@@ -350,14 +356,14 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
     v.tok_emb = emb; v.tokp = tokp; v.x = c->x; v.rms_w = rms_w;
     v.xh = c->XhD; v.xl = c->XlD; v.D = D;
     void* args[] = {&v};
-    return launch(c, L2B_K_WO, (const void*)bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
+    return launch(c, L2B_K_BATCH_EPI, (const void*)bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
   };
 
   rc = resid_rms(nullptr, 0, c->tok_emb, c->rms_att);  // x := embedding; rmsnorm of layer 0
   if (rc) return rc;
   const int cs = auto_cluster(c, B);
   for (int l = 0; l < c->L; ++l) {
-    rc = launch_gemm(c, L2B_K_QKV, c->wqkv + (size_t)l * 3 * D * D, 3 * D, D, c->XhD, c->XlD, B, &S, st);
+    rc = launch_gemm(c, L2B_K_GEMM_QKV, c->wqkv + (size_t)l * 3 * D * D, 3 * D, D, c->XhD, c->XlD, B, &S, st);
     if (rc) return rc;
     {
       BatQkvParams q;
@@ -367,7 +373,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
       q.kc = c->kc + (size_t)l * kv_layer; q.vc = c->vc + (size_t)l * kv_layer;
       q.kv_seq_stride = (long long)kv_seq;
       void* args[] = {&q};
-      rc = launch(c, L2B_K_QKV, (const void*)bat_qkv_epi_kernel, dim3((3 * D / 2 + 255) / 256, B), dim3(256), 0,
+      rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_qkv_epi_kernel, dim3((3 * D / 2 + 255) / 256, B), dim3(256), 0,
                   1, args, st);
       if (rc) return rc;
     }
@@ -391,27 +397,27 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
                   args, st);
       if (rc) return rc;
     }
-    rc = launch_gemm(c, L2B_K_WO, c->wo + (size_t)l * D * D, D, D, c->XhD, c->XlD, B, &S, st);
+    rc = launch_gemm(c, L2B_K_GEMM_WO, c->wo + (size_t)l * D * D, D, D, c->XhD, c->XlD, B, &S, st);
     if (rc) return rc;
     rc = resid_rms(c->P, S, nullptr, c->rms_ffn + (size_t)l * D);
     if (rc) return rc;
-    rc = launch_gemm(c, L2B_K_W13, c->w13 + (size_t)l * 2 * F * D, 2 * F, D, c->XhD, c->XlD, B, &S, st);
+    rc = launch_gemm(c, L2B_K_GEMM_W13, c->w13 + (size_t)l * 2 * F * D, 2 * F, D, c->XhD, c->XlD, B, &S, st);
     if (rc) return rc;
     {
       BatSwigluParams w;
       memset(&w, 0, sizeof w);
       w.P = c->P; w.S = S; w.B = B; w.F = F; w.xh = c->XhF; w.xl = c->XlF;
       void* args[] = {&w};
-      rc = launch(c, L2B_K_W13, (const void*)bat_swiglu_kernel, dim3((F + 255) / 256, B), dim3(256), 0, 1, args,
+      rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_swiglu_kernel, dim3((F + 255) / 256, B), dim3(256), 0, 1, args,
                   st);
       if (rc) return rc;
     }
-    rc = launch_gemm(c, L2B_K_W2, c->w2 + (size_t)l * D * F, D, F, c->XhF, c->XlF, B, &S, st);
+    rc = launch_gemm(c, L2B_K_GEMM_W2, c->w2 + (size_t)l * D * F, D, F, c->XhF, c->XlF, B, &S, st);
     if (rc) return rc;
     rc = resid_rms(c->P, S, nullptr, l + 1 < c->L ? c->rms_att + (size_t)(l + 1) * D : c->rms_final);
     if (rc) return rc;
   }
-  rc = launch_gemm(c, L2B_K_CLS, c->wcls, V, D, c->XhD, c->XlD, B, &S, st);
+  rc = launch_gemm(c, L2B_K_GEMM_CLS, c->wcls, V, D, c->XhD, c->XlD, B, &S, st);
   if (rc) return rc;
   {
     BatLogitsParams g;
@@ -419,11 +425,11 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
     g.P = c->P; g.S = S; g.B = B; g.V = V; g.logits = c->logits; g.ctl = c->d_ctl;
     g.next = c->d_dev + 1; g.forced = c->d_forced; g.out_tokens = c->d_out;
     void* args[] = {&g};
-    rc = launch(c, L2B_K_CLS, (const void*)bat_logits_kernel, dim3(B), dim3(1024), 0, 1, args, st);
+    rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_logits_kernel, dim3(B), dim3(1024), 0, 1, args, st);
     if (rc) return rc;
     int* ctl = c->d_ctl;
     void* args2[] = {&ctl};
-    rc = launch(c, L2B_K_CLS, (const void*)bat_step_kernel, dim3(1), dim3(32), 0, 1, args2, st);
+    rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_step_kernel, dim3(1), dim3(32), 0, 1, args2, st);
     if (rc) return rc;
   }
   return 0;
@@ -734,7 +740,7 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
   const size_t max_grid = (size_t)c->num_sms * 4;
   TRY(dev_alloc(c, &c->blk_val, max_grid * kMaxNB, true));
   TRY(dev_alloc(c, &c->blk_idx, max_grid * kMaxNB, true));
-  if (max_batch > kMaxNB) {
+  if (max_batch >= 5) {
     // tensor-core path scratch: activations padded to whole 256-column groups
     c->Bpad = ((max_batch + 255) / 256) * 256;
     const size_t Mmax = (size_t)(3 * D > 2 * F ? 3 * D : 2 * F) > sV ? (size_t)(3 * D > 2 * F ? 3 * D : 2 * F) : sV;
@@ -926,18 +932,18 @@ L2B_API int l2b_generate_greedy(l2b_ctx* c, int32_t B, const int32_t* tokens, co
 L2B_API float l2b_last_device_ms(const l2b_ctx* c) { return c ? c->last_ms : 0.f; }
 L2B_API int64_t l2b_last_launches(const l2b_ctx* c) { return c ? c->last_launches : 0; }
 
-L2B_API int l2b_profile_step(l2b_ctx* c, int32_t token, int32_t pos, float* ms_per_class,
-                             int32_t* launches_per_class) {
+L2B_API int l2b_profile_batch(l2b_ctx* c, int32_t B, const int32_t* tokens, const int32_t* pos,
+                              float* ms_per_class, int32_t* launches_per_class) {
   int rc = check_ready(c);
   if (rc) return rc;
   if (!ms_per_class || !launches_per_class) return fail(c, L2B_EINVAL, "null output");
   CU(c, cudaSetDevice(c->device));
-  rc = stage_inputs(c, 1, &token, &pos, 0, 0, 0, 1);
+  rc = stage_inputs(c, B, tokens, pos, 0, 0, 0, 1);
   if (rc) return rc;
   c->profiling = true;
   c->prof_events.clear();
   c->prof_class.clear();
-  rc = run_steps(c, 1, 1);
+  rc = run_steps(c, B, 1);
   c->profiling = false;
   if (!rc) {
     cudaEvent_t e;
@@ -957,12 +963,17 @@ L2B_API int l2b_profile_step(l2b_ctx* c, int32_t token, int32_t pos, float* ms_p
       ms_per_class[c->prof_class[i]] += ms;
       launches_per_class[c->prof_class[i]] += 1;
     }
-    mark_run(c, 1, &pos, 1);
+    mark_run(c, B, pos, 1);
   }
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   c->prof_events.clear();
   c->prof_class.clear();
   return rc;
+}
+
+L2B_API int l2b_profile_step(l2b_ctx* c, int32_t token, int32_t pos, float* ms_per_class,
+                             int32_t* launches_per_class) {
+  return l2b_profile_batch(c, 1, &token, &pos, ms_per_class, launches_per_class);
 }
 
 L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer, int32_t pos,
@@ -1036,6 +1047,8 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.evict_first = v < 0 ? -1 : (v != 0);
   } else if (k == "tc_min_batch") {
     o.tc_min_batch = v < 0 ? 0 : v;
+  } else if (k == "tc_rewrite_hi") {
+    o.tc_rewrite_hi = v != 0;
   } else if (k == "tc_splits") {
     o.tc_splits = v < 0 ? 0 : v;
   } else {

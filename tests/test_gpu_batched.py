@@ -51,6 +51,14 @@ def test_k_splits(pkg, oracle, splits):
     print("splits=%d: max|dlogit| %.3g" % (splits, worst))
 
 
+@pytest.mark.parametrize("B", [20, 200])
+def test_weight_hi_rounding_variant(pkg, oracle, B):
+    """tc_rewrite_hi=1: the weights' hi part is rounded to nearest and rewritten in shared
+    memory instead of relying on the tensor core truncating the raw fp32 tile."""
+    worst, _ = run_batch(pkg, oracle, "wide", B, 5, 23, 0.03, opts=(("tc_rewrite_hi", 1),))
+    print("rewrite_hi B=%d: max|dlogit| %.3g" % (B, worst))
+
+
 def test_batched_greedy_loop_matches_gemv_path(pkg, oracle):
     """Device-resident greedy loop for B sequences: tensor-core path and the fp64 GEMV path
     (tc_min_batch=0) must emit the same token streams as B separate reference loops."""
@@ -67,7 +75,7 @@ def test_batched_greedy_loop_matches_gemv_path(pkg, oracle):
         out, _ = m.generate(steps, [int(first[b])], temperature=0.0)
         want.append(out)
     oracle.set_threads(1)
-    for tc in (9, 0):
+    for tc in (5, 0):
         ctx = pkg.Context(hdr, max_batch=B, max_steps=steps)
         pkg.synth.upload_blob(ctx, hdr, blob)
         ctx.set_option("tc_min_batch", tc)

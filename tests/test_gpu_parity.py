@@ -154,14 +154,16 @@ def test_variants_agree(pkg, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("B", [2, 3, 5, 8, 11])
-def test_batch_independent_sequences(pkg, oracle, B):
-    """B independent RunStates advanced in lock-step but at DIFFERENT positions."""
+@pytest.mark.parametrize("B,tc", [(2, 0), (3, 0), (5, 0), (8, 0), (11, 0), (5, 5), (11, 5)])
+def test_batch_independent_sequences(pkg, oracle, B, tc):
+    """B independent RunStates advanced in lock-step but at DIFFERENT positions; tc=0 forces the
+    multi-sequence fp64 GEMV kernels, tc=5 is the default (tensor cores from 5 sequences up)."""
     hdr = pkg.synth.header("small")
     _, blob = pkg.synth.checkpoint_blob(hdr, seed=9, std=0.05)
     V = abs(hdr[5])
     ctx = pkg.Context(hdr, max_batch=B, max_steps=24)
     pkg.synth.upload_blob(ctx, hdr, blob)
+    ctx.set_option("tc_min_batch", tc)
     refs = [oracle.Model(hdr, blob) for _ in range(B)]
     streams = [np.concatenate([[1], pkg.synth.teacher_tokens(23, V, 100 + b)]) for b in range(B)]
     # stagger: sequence b starts b % 3 steps late (pos differs across the batch)
