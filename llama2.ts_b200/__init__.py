@@ -14,5 +14,5 @@ The directory name contains a dot, so import it through the root shim:
 ``import llama2_ts_b200``.  There is no CPU fallback anywhere in this package:
 without the built library or without a B200 every compute call raises.
 """
-from . import build, capi, host, synth  # noqa: F401
+from . import build, capi, dist, host, synth  # noqa: F401
 from .capi import L2BError, Library, Context  # noqa: F401
