@@ -64,7 +64,7 @@ _SIGNATURES = {
     "l2b_reset": (C.c_int, [_p]),
     "l2b_set_option": (C.c_int, [_p, C.c_char_p, _i64]),
     "l2b_tp_export": (_i64, [_p, _p, _u64]),
-    "l2b_tp_connect": (C.c_int, [_p, _p, _u64, _i32]),
+    "l2b_tp_connect": (C.c_int, [_p, C.c_char_p, _u64, _i32]),
     "l2b_last_error": (C.c_char_p, [_p]),
     "l2b_abi_version": (C.c_int, []),
     "l2b_destroy": (None, [_p]),
@@ -117,7 +117,9 @@ def _ptr(a):
 class Context:
     """One l2b_ctx: weights + RunState(s) + KV cache on one B200."""
 
-    def __init__(self, hdr, device=0, max_batch=1, max_steps=0, lib=None):
+    def __init__(self, hdr, device=0, max_batch=1, max_steps=0, lib=None, tp_rank=0, tp_size=1):
+        """tp_size > 1: this process is rank `tp_rank` of a row-sharded tensor-parallel group
+        (l2b_create_tp); call tp_export()/tp_connect() (or dist.connect_tp) before the first step."""
         self.lib = lib or Library.get()
         self.hdr = [int(v) for v in hdr]
         assert len(self.hdr) == 7
@@ -129,7 +131,11 @@ class Context:
         self.max_steps = max_steps or self.seq_len
         h = (_i32 * 7)(*self.hdr)
         out = _p()
-        rc = self.lib.dll.l2b_create(h, device, max_batch, max_steps, C.byref(out))
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        if tp_size > 1:
+            rc = self.lib.dll.l2b_create_tp(h, device, max_steps, tp_rank, tp_size, C.byref(out))
+        else:
+            rc = self.lib.dll.l2b_create(h, device, max_batch, max_steps, C.byref(out))
         if rc != 0:
             raise L2BError(rc, self.lib.dll.l2b_last_error(None).decode())
         self._h = out
@@ -236,6 +242,21 @@ class Context:
         out = np.empty(n, dtype=np.float32)
         self._check(self.lib.dll.l2b_read_state(self._h, which, seq, layer, pos, _ptr(out), n))
         return out
+
+    def tp_export(self):
+        """Opaque handle blob of this rank's exchange block (bytes)."""
+        buf = C.create_string_buffer(256)
+        n = self.lib.dll.l2b_tp_export(self._h, buf, 256)
+        if n < 0:
+            self._check(int(n))
+        return buf.raw[:n]
+
+    def tp_connect(self, blobs):
+        """blobs: list of every rank's tp_export() in rank order."""
+        n = len(blobs[0])
+        assert all(len(b) == n for b in blobs)
+        joined = b"".join(blobs)
+        self._check(self.lib.dll.l2b_tp_connect(self._h, joined, n, len(blobs)))
 
     def reset(self):
         self._check(self.lib.dll.l2b_reset(self._h))

@@ -44,6 +44,40 @@ enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
 constexpr int kU = 4;          // float4 loads per lane per row per tile
 constexpr int kMaxNB = 8;      // sequences sharing one weight pass
 
+// Tensor-parallel exchange (row-sharded projections).  Every rank
+// holds replicas of the gathered vectors (x, xb, hb, logits); a kernel's epilogue stores its
+// slice straight into EVERY peer's replica over NVLink (peer-mapped pointers) and the last
+// CTA publishes a sequence number to every peer's flag word; the consumer kernel spins on its
+// local flags before it reads the gathered vector.  No NCCL launch on the critical path.
+constexpr int kMaxTp = 8;
+struct TpParams {
+  int rank, size;
+  const int* epoch;            // device word: sequence base of the current step
+  const int* wait_flags;       // local flags[e_in][0..size) to wait on, or nullptr
+  int wait_idx;                // e_in
+  int out_idx;                 // e_out
+  int out_off;                 // rank * slice: where this rank's results sit in the gathered vector
+  int* ticket;                 // local ticket counter (last CTA publishes)
+  int* err;                    // local error word (set on a wait time-out)
+  int* peer_flags[kMaxTp];     // &peer.flags[e_out][rank]
+  float* peer_out[kMaxTp];     // peer replicas of the output vector
+  float* peer_am_val[kMaxTp];  // classifier: per-rank argmax candidates on every peer
+  int* peer_am_idx[kMaxTp];
+};
+
+// bounded spin on a flag written by a peer (about 2 s, then the error word is set so that the
+// host reports L2B_ECOMM instead of hanging the GPU)
+__device__ __forceinline__ void tp_wait_flag(const int* f, int seq, int* err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys_i32(f) < seq) {
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000LL) {
+      atomicExch(err, 1);
+      break;
+    }
+  }
+}
+
 struct GemvParams {
   const float* W;        // [rows][n] row-major, rows even
   int rows;
@@ -80,6 +114,7 @@ struct GemvParams {
   // batch slice handled by this launch
   int b0, nact, B;
   int evict_first;
+  TpParams tp;           // used by the TP = true instantiations only
 };
 
 // host-written control header (ints)
@@ -155,7 +190,7 @@ __device__ __forceinline__ void argmax_consider(float v, int i, float& bv, int& 
   }
 }
 
-template <int PRO, int EPI, int NB, int THREADS, bool F64>
+template <int PRO, int EPI, int NB, int THREADS, bool F64, bool TP = false>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 && NB <= 2) ? 2 : 1)
 gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
   constexpr int WARPS = THREADS / 32;
@@ -192,6 +227,14 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
 
   // ---- everything below may depend on the previous kernel ----
   griddep_wait();
+  int tp_seq = 0;
+  if (TP) {
+    tp_seq = ld_act_i32(p.tp.epoch) + 1;
+    if (p.tp.wait_flags != nullptr) {  // the gathered input must have arrived from every rank
+      if ((int)threadIdx.x < p.tp.size) tp_wait_flag(p.tp.wait_flags + threadIdx.x, tp_seq + p.tp.wait_idx, p.tp.err);
+      __syncthreads();
+    }
+  }
 
   // prologue: build the activation vector(s) in shared memory
   {
@@ -353,26 +396,67 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
           }
         } else if (EPI == EPI_RESID) {
           // accum(x, xb2), llama2.ts:168-170,273,295
-          float* xr = p.x + (size_t)eb * p.xdim + r;
-          xr[0] = (float)((double)xr[0] + (double)s0);
-          xr[1] = (float)((double)xr[1] + (double)s1);
+          if (TP) {
+            const int gi = p.tp.out_off + r;  // index in the replicated residual stream
+            const float n0 = (float)((double)ld_act(p.x + gi) + (double)s0);
+            const float n1 = (float)((double)ld_act(p.x + gi + 1) + (double)s1);
+            for (int g = 0; g < p.tp.size; ++g) {
+              st_relaxed_sys_f32(p.tp.peer_out[g] + gi, n0);
+              st_relaxed_sys_f32(p.tp.peer_out[g] + gi + 1, n1);
+            }
+          } else {
+            float* xr = p.x + (size_t)eb * p.xdim + r;
+            xr[0] = (float)((double)xr[0] + (double)s0);
+            xr[1] = (float)((double)xr[1] + (double)s1);
+          }
         } else if (EPI == EPI_SWIGLU) {
           // rows interleaved on upload: 2i = w1 row i, 2i+1 = w3 row i.  llama2.ts:284-289
           const double hv = (double)s0;
           const float silu = (float)(hv * (1.0 / (1.0 + exp(-hv))));
-          p.hb[(size_t)eb * p.hb_stride + pair] = (float)((double)silu * (double)s1);
+          const float hv2 = (float)((double)silu * (double)s1);
+          if (TP) {
+            for (int g = 0; g < p.tp.size; ++g) st_relaxed_sys_f32(p.tp.peer_out[g] + p.tp.out_off + pair, hv2);
+          } else {
+            p.hb[(size_t)eb * p.hb_stride + pair] = hv2;
+          }
         } else {
-          float* lg = p.logits + (size_t)eb * p.V + r;
-          lg[0] = s0;
-          lg[1] = s1;
-          argmax_consider(s0, r, bv, bi);
-          argmax_consider(s1, r + 1, bv, bi);
+          if (TP) {
+            for (int g = 0; g < p.tp.size; ++g) {
+              st_relaxed_sys_f32(p.tp.peer_out[g] + p.tp.out_off + r, s0);
+              st_relaxed_sys_f32(p.tp.peer_out[g] + p.tp.out_off + r + 1, s1);
+            }
+            argmax_consider(s0, p.tp.out_off + r, bv, bi);      // global vocabulary index
+            argmax_consider(s1, p.tp.out_off + r + 1, bv, bi);
+          } else {
+            float* lg = p.logits + (size_t)eb * p.V + r;
+            lg[0] = s0;
+            lg[1] = s1;
+            argmax_consider(s0, r, bv, bi);
+            argmax_consider(s1, r + 1, bv, bi);
+          }
         }
       }
     }
     pair = npair;
     jt = njt;
     cur = nxt;
+  }
+
+  if (TP && (EPI == EPI_RESID || EPI == EPI_SWIGLU)) {
+    // publish: every remote store of this CTA is ordered before its ticket; the last CTA
+    // raises this rank's flag on every peer
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int t = atomicAdd(p.tp.ticket, 1);
+      s_is_last = (t == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_is_last) {
+      __threadfence_system();
+      if ((int)threadIdx.x < p.tp.size) st_release_sys_i32(p.tp.peer_flags[threadIdx.x], tp_seq + p.tp.out_idx);
+      if (threadIdx.x == 0) *p.tp.ticket = 0;
+    }
   }
 
   if (EPI == EPI_LOGITS) {
@@ -391,13 +475,38 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
       p.blk_idx[blockIdx.x * kMaxNB + s] = i;
       __threadfence();
     }
+    if (TP) __threadfence_system();  // the logits slice stored into the peers
     __syncthreads();
     if (threadIdx.x == 0) {
       const int t = atomicAdd(p.ticket, 1);
       s_is_last = (t == (int)gridDim.x - 1);
     }
     __syncthreads();
-    if (s_is_last && warp == 0) {
+    if (TP) {
+      // rank-local candidate -> every peer; tp_finalize_kernel picks the global first maximum
+      if (s_is_last && warp == 0) {
+        __threadfence();
+        float v = -INFINITY;
+        int i = 0x7fffffff;
+        for (int g = lane; g < (int)gridDim.x; g += 32)
+          argmax_consider(ld_act(p.blk_val + g * kMaxNB), ld_act_i32(p.blk_idx + g * kMaxNB), v, i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+          argmax_consider(ov, oi, v, i);
+        }
+        if (lane < p.tp.size) {
+          st_relaxed_sys_f32(p.tp.peer_am_val[lane] + p.tp.rank, v);
+          asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.tp.peer_am_idx[lane] + p.tp.rank), "r"(i)
+                       : "memory");
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < p.tp.size) st_release_sys_i32(p.tp.peer_flags[lane], tp_seq + p.tp.out_idx);
+        if (lane == 0) *p.ticket = 0;
+      }
+    } else if (s_is_last && warp == 0) {
       __threadfence();
       const int B = p.B;
       const int step = ld_act_i32(p.ctl + CTL_STEP);
@@ -472,8 +581,12 @@ struct AttnParams {
   int tileT;         // time steps per ring stage
   int sc_cap;        // floats reserved for scores per CTA
   // tensor-parallel all-gather of the output slice (nullptr when tp_size == 1)
-  float* const* peer_xb;  // [tp_size] peers' xb buffers (including our own)
+  float* peer_xb[kMaxTp];  // peers' xb replicas (including our own)
   int tp_size;
+  const int* tp_epoch;     // device word: sequence base of the current step
+  int tp_out_idx;          // exchange index of this all-gather
+  int* tp_ticket;          // local ticket counter
+  int* tp_peer_flags[kMaxTp];
   // batched tensor-core path: also emit the TF32 hi/lo split of the output (input of the wo GEMM)
   float* xh;
   float* xl;
@@ -686,7 +799,72 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
       for (int r = 0; r < p.tp_size; ++r) st_relaxed_sys_f32(p.peer_xb[r] + o, s);
     }
   }
+  if (p.tp_size > 1 && rank == 0) {
+    // all-gather publication: last (sequence, head) leader raises this rank's flag on every peer
+    __shared__ int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const int t = atomicAdd(p.tp_ticket, 1);
+      s_last = (t == (int)(gridDim.y * gridDim.z) - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence_system();
+      const int seq = ld_act_i32(p.tp_epoch) + 1 + p.tp_out_idx;
+      if (tid < p.tp_size) st_release_sys_i32(p.tp_peer_flags[tid], seq);
+      if (tid == 0) *p.tp_ticket = 0;
+    }
+  }
   cluster_sync_all();  // keep every CTA's shared memory alive until rank 0 has read it
+}
+
+// Tensor-parallel step epilogue (one warp): waits for every rank's classifier slice, picks
+// the global argmax (llama2.ts:364-366: first maximum wins -> lowest global index), runs the
+// state machine of llama2.ts:471-504 on this rank's replica of the control block and moves
+// the exchange epoch on.  Every rank computes the same token.
+struct TpFinalParams {
+  int size, n_exchanges;
+  int* epoch;
+  const int* wait_flags;   // local flags[last exchange][0..size)
+  int wait_idx;
+  const float* am_val;     // [size] candidates written by the ranks
+  const int* am_idx;
+  const float* logits;     // local replica of the gathered logits
+  int* ctl;
+  int* next;
+  const int* forced;
+  int* out_tokens;
+  int* err;
+};
+__global__ void tp_finalize_kernel(const __grid_constant__ TpFinalParams p) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int lane = threadIdx.x;
+  const int base = ld_act_i32(p.epoch);
+  if (lane < p.size) tp_wait_flag(p.wait_flags + lane, base + 1 + p.wait_idx, p.err);
+  __syncwarp();
+  if (lane == 0) {
+    float v = -INFINITY;
+    int i = 0x7fffffff;
+    for (int g = 0; g < p.size; ++g) argmax_consider(ld_act(p.am_val + g), ld_act_i32(p.am_idx + g), v, i);
+    const float l0 = ld_act(p.logits);
+    if (i == 0x7fffffff || l0 != l0) i = 0;
+    const int step = p.ctl[CTL_STEP];
+    int chosen = i;
+    if (p.ctl[CTL_USE_FORCED]) {
+      const int f = p.forced[step];
+      if (f >= 0) chosen = f;
+    }
+    p.next[0] = i;
+    p.out_tokens[step] = chosen;
+    if (p.ctl[CTL_ADVANCE]) {
+      p.ctl[CTL_HDR] = chosen;
+      p.ctl[CTL_HDR + 1] = p.ctl[CTL_HDR + 1] + 1;
+      p.ctl[CTL_STEP] = step + 1;
+    }
+    *p.epoch = base + p.n_exchanges;
+  }
 }
 
 }  // namespace l2b

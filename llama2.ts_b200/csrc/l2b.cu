@@ -50,8 +50,16 @@ struct l2b_ctx {
   bool shared_cls = false;
   int device = 0, num_sms = 148;
   int Bmax = 1, steps = 0;
-  // tensor parallel
+  // tensor parallel (row-sharded projections, one process per GPU)
   int tp_rank = 0, tp_size = 1;
+  int Dl = 0, Fl = 0, Vl = 0, Hl = 0;   // this rank's slice of dim / hidden / vocab / heads
+  unsigned char* xchg = nullptr;         // exchange block: x | xb | hb | logits | am_val | am_idx | flags
+  size_t xchg_bytes = 0;
+  size_t off_x = 0, off_xb = 0, off_hb = 0, off_logits = 0, off_amv = 0, off_ami = 0, off_flags = 0;
+  unsigned char* peer[kMaxTp] = {nullptr};  // peers' exchange blocks (peer[tp_rank] == xchg)
+  bool tp_connected = false;
+  int *tp_epoch = nullptr, *tp_ticket = nullptr, *tp_err = nullptr;
+  int* h_err = nullptr;
   // weights
   float *tok_emb = nullptr, *rms_att = nullptr, *wqkv = nullptr, *wo = nullptr, *rms_ffn = nullptr,
         *w13 = nullptr, *w2 = nullptr, *rms_final = nullptr, *fcr = nullptr, *fci = nullptr,
@@ -165,6 +173,17 @@ gemv_fn pick_kernel(int kc, int nb, int threads, bool f64) {
   return nullptr;
 }
 
+gemv_fn pick_kernel_tp(int kc) {
+  switch (kc) {
+    case L2B_K_QKV: return (gemv_fn)gemv_pairs_kernel<PRO_RMS, EPI_QKV, 1, 512, true, true>;
+    case L2B_K_WO:
+    case L2B_K_W2: return (gemv_fn)gemv_pairs_kernel<PRO_COPY, EPI_RESID, 1, 512, true, true>;
+    case L2B_K_W13: return (gemv_fn)gemv_pairs_kernel<PRO_RMS, EPI_SWIGLU, 1, 512, true, true>;
+    case L2B_K_CLS: return (gemv_fn)gemv_pairs_kernel<PRO_RMS, EPI_LOGITS, 1, 512, true, true>;
+  }
+  return nullptr;
+}
+
 int launch(l2b_ctx* c, int kclass, const void* fn, dim3 grid, dim3 block, size_t smem,
            int cluster_x, void** args, cudaStream_t st) {
   if (!c->smem_set.count(fn)) {
@@ -218,6 +237,12 @@ int pick_nb(const l2b_ctx* c, int B, int n) {
 }
 
 int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
+  if (c->tp_size > 1) {
+    gemv_fn fn = pick_kernel_tp(kclass);
+    p.B = 1; p.b0 = 0; p.nact = 1;
+    void* args[] = {&p};
+    return launch(c, kclass, (const void*)fn, dim3(c->num_sms), dim3(512), (size_t)p.n * 8, 1, args, st);
+  }
   const int nb = pick_nb(c, B, p.n);
   int threads = c->opt.threads;
   if (nb >= 4) threads = 256;
@@ -435,8 +460,184 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
   return 0;
 }
 
+// ---- tensor-parallel step (batch 1, row-sharded projections, in-kernel NVLink exchange) -----
+int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
+  const int D = c->D, F = c->F, hs = c->hs, G = c->tp_size, R = c->tp_rank;
+  const int Dl = c->Dl, Fl = c->Fl, Vl = c->Vl, Hl = c->Hl, L = c->L;
+  const size_t kv_seq = (size_t)Hl * c->steps * hs;
+  int ef = c->opt.evict_first;
+  if (ef < 0) ef = c->weight_bytes > (size_t)100 * 1024 * 1024;
+
+  auto flag_on = [&](int g, int e, int src) { return (int*)(c->peer[g] + c->off_flags) + (size_t)e * kMaxTp + src; };
+  auto fill_tp = [&](TpParams& t, int wait_e, int out_e, size_t out_vec_off, int out_off) {
+    memset(&t, 0, sizeof t);
+    t.rank = R; t.size = G;
+    t.epoch = c->tp_epoch; t.ticket = c->tp_ticket; t.err = c->tp_err;
+    t.wait_flags = wait_e >= 0 ? flag_on(R, wait_e, 0) : nullptr;
+    t.wait_idx = wait_e < 0 ? 0 : wait_e;
+    t.out_idx = out_e < 0 ? 0 : out_e;
+    t.out_off = out_off;
+    for (int g = 0; g < G; ++g) {
+      t.peer_flags[g] = out_e >= 0 ? flag_on(g, out_e, R) : nullptr;
+      t.peer_out[g] = (float*)(c->peer[g] + out_vec_off);
+      t.peer_am_val[g] = (float*)(c->peer[g] + c->off_amv);
+      t.peer_am_idx[g] = (int*)(c->peer[g] + c->off_ami);
+    }
+  };
+
+  GemvParams base;
+  memset(&base, 0, sizeof base);
+  base.tokp = c->d_ctl + CTL_HDR;
+  base.posp = c->d_ctl + CTL_HDR + 1;
+  base.x = c->x;
+  base.xdim = D;
+  base.fcr = c->fcr;
+  base.fci = c->fci;
+  base.hs = hs;
+  base.steps = c->steps;
+  base.kv_seq_stride = (long long)kv_seq;
+  base.ctl = c->d_ctl;
+  base.ticket = c->d_dev;
+  base.next = c->d_dev + 1;
+  base.forced = c->d_forced;
+  base.out_tokens = c->d_out;
+  base.blk_val = c->blk_val;
+  base.blk_idx = c->blk_idx;
+  base.evict_first = ef;
+
+  // same time-step split as the single-GPU launch, so the attention sums associate identically
+  int cs = c->opt.attn_cluster;
+  if (cs <= 0) {
+    cs = 8;
+    while (cs > 1 && c->H * cs > c->num_sms) cs >>= 1;
+  }
+  for (int l = 0; l < L; ++l) {
+    const int eA = 4 * l, eB = 4 * l + 1, eC = 4 * l + 2, eD = 4 * l + 3;
+    {  // rmsnorm -> this rank's heads of q,k,v -> RoPE -> KV write (needs x from every rank)
+      GemvParams p = base;
+      p.W = c->wqkv + (size_t)l * 3 * Dl * D;
+      p.rows = 3 * Dl;
+      p.n = D;
+      p.vin = c->x;
+      p.vin_stride = D;
+      p.rms_w = c->rms_att + (size_t)l * D;
+      p.tok_emb = (l == 0) ? c->tok_emb : nullptr;
+      p.q = c->q;
+      p.kc = c->kc + (size_t)l * kv_seq;
+      p.vc = c->vc + (size_t)l * kv_seq;
+      p.Dq = Dl;
+      fill_tp(p.tp, l == 0 ? -1 : eD - 4, -1, c->off_x, 0);
+      int rc = launch_gemv(c, L2B_K_QKV, p, 1, st);
+      if (rc) return rc;
+    }
+    {  // attention over this rank's heads; output slice all-gathered into every replica of xb
+      AttnParams a;
+      memset(&a, 0, sizeof a);
+      a.q = c->q;
+      a.kc = c->kc + (size_t)l * kv_seq;
+      a.vc = c->vc + (size_t)l * kv_seq;
+      a.xb = c->xb;
+      a.posp = c->d_ctl + CTL_HDR + 1;
+      a.H = Hl;
+      a.hs = hs;
+      a.steps = c->steps;
+      a.q_stride = Dl;
+      a.xb_stride = D;
+      a.xb_off = R * Dl;
+      a.tileT = kAttnStageBytes / (hs * 4);
+      a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
+      a.tp_size = G;
+      a.tp_epoch = c->tp_epoch;
+      a.tp_out_idx = eA;
+      a.tp_ticket = c->tp_ticket;
+      for (int g = 0; g < G; ++g) {
+        a.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
+        a.tp_peer_flags[g] = flag_on(g, eA, R);
+      }
+      const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
+      void* args[] = {&a};
+      int rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, Hl, 1), dim3(kAttnThreads), smem,
+                      cs, args, st);
+      if (rc) return rc;
+    }
+    {  // rows [R*Dl, (R+1)*Dl) of wo + residual -> every replica of x
+      GemvParams p = base;
+      p.W = c->wo + (size_t)l * Dl * D;
+      p.rows = Dl;
+      p.n = D;
+      p.vin = c->xb;
+      p.vin_stride = D;
+      fill_tp(p.tp, eA, eB, c->off_x, R * Dl);
+      int rc = launch_gemv(c, L2B_K_WO, p, 1, st);
+      if (rc) return rc;
+    }
+    {  // this rank's hidden units of w1/w3 -> SwiGLU -> every replica of hb
+      GemvParams p = base;
+      p.W = c->w13 + (size_t)l * 2 * Fl * D;
+      p.rows = 2 * Fl;
+      p.n = D;
+      p.vin = c->x;
+      p.vin_stride = D;
+      p.rms_w = c->rms_ffn + (size_t)l * D;
+      p.hb = c->hb;
+      p.hb_stride = F;
+      fill_tp(p.tp, eB, eC, c->off_hb, R * Fl);
+      int rc = launch_gemv(c, L2B_K_W13, p, 1, st);
+      if (rc) return rc;
+    }
+    {  // rows of w2 + residual -> every replica of x
+      GemvParams p = base;
+      p.W = c->w2 + (size_t)l * Dl * F;
+      p.rows = Dl;
+      p.n = F;
+      p.vin = c->hb;
+      p.vin_stride = F;
+      fill_tp(p.tp, eC, eD, c->off_x, R * Dl);
+      int rc = launch_gemv(c, L2B_K_W2, p, 1, st);
+      if (rc) return rc;
+    }
+  }
+  const int eE = 4 * L;
+  {  // this rank's vocabulary rows -> every replica of logits + per-rank argmax candidate
+    GemvParams p = base;
+    p.W = c->wcls;
+    p.rows = Vl;
+    p.n = D;
+    p.vin = c->x;
+    p.vin_stride = D;
+    p.rms_w = c->rms_final;
+    p.logits = c->logits;
+    p.V = c->V;
+    fill_tp(p.tp, eE - 1, eE, c->off_logits, R * Vl);
+    int rc = launch_gemv(c, L2B_K_CLS, p, 1, st);
+    if (rc) return rc;
+  }
+  {
+    TpFinalParams f;
+    memset(&f, 0, sizeof f);
+    f.size = G;
+    f.n_exchanges = 4 * L + 1;
+    f.epoch = c->tp_epoch;
+    f.wait_flags = flag_on(R, eE, 0);
+    f.wait_idx = eE;
+    f.am_val = (const float*)(c->xchg + c->off_amv);
+    f.am_idx = (const int*)(c->xchg + c->off_ami);
+    f.logits = c->logits;
+    f.ctl = c->d_ctl;
+    f.next = c->d_dev + 1;
+    f.forced = c->d_forced;
+    f.out_tokens = c->d_out;
+    f.err = c->tp_err;
+    void* args[] = {&f};
+    int rc = launch(c, L2B_K_CLS, (const void*)tp_finalize_kernel, dim3(1), dim3(32), 0, 1, args, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 // One decode step for B sequences: tokens/positions are read from d_ctl.
 int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
+  if (c->tp_size > 1) return enqueue_step_tp(c, st);
   if (c->opt.tc_min_batch > 0 && B >= c->opt.tc_min_batch && c->P != nullptr)
     return enqueue_step_batched(c, B, st);
   const int D = c->D, F = c->F, hs = c->hs, H = c->H;
@@ -499,7 +700,6 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       a.xb_off = 0;
       a.tileT = kAttnStageBytes / (hs * 4);
       a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
-      a.peer_xb = nullptr;
       a.tp_size = 1;
       const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
@@ -605,14 +805,22 @@ int run_steps(l2b_ctx* c, int B, int n_steps) {
 }
 
 int finish(l2b_ctx* c) {
+  if (c->tp_size > 1)
+    CU(c, cudaMemcpyAsync(c->h_err, c->tp_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   CU(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  if (c->tp_size > 1 && *c->h_err != 0) {
+    cudaMemsetAsync(c->tp_err, 0, sizeof(int), c->stream);
+    return fail(c, L2B_ECOMM, "tensor-parallel exchange timed out waiting for a peer rank");
+  }
   return 0;
 }
 
 int check_ready(l2b_ctx* c) {
   if (!c) return L2B_EINVAL;
   if (!l2b_weights_ready(c)) return fail(c, L2B_ESTATE, "weights not fully uploaded");
+  if (c->tp_size > 1 && !c->tp_connected)
+    return fail(c, L2B_ESTATE, "tensor-parallel context not connected (l2b_tp_export / l2b_tp_connect)");
   return 0;
 }
 
@@ -678,8 +886,10 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
   if (max_batch < 1) return fail(nullptr, L2B_EINVAL, "max_batch must be >= 1");
   if (max_steps < 0 || max_steps > S) return fail(nullptr, L2B_EINVAL, "max_steps outside [0,seq_len]");
   if (max_steps == 0) max_steps = S;
-  if (tp_size != 1) return fail(nullptr, L2B_EINVAL, "tensor parallel degree %d not supported", tp_size);
-  (void)tp_rank;
+  if (tp_size < 1 || tp_size > kMaxTp || tp_rank < 0 || tp_rank >= tp_size)
+    return fail(nullptr, L2B_EINVAL, "tensor parallel rank %d of %d", tp_rank, tp_size);
+  if (tp_size > 1 && (H % tp_size || F % tp_size || V % (2 * tp_size) || (D / tp_size) % 2))
+    return fail(nullptr, L2B_EINVAL, "heads, hidden_dim and vocab/2 must be divisible by the tensor-parallel degree");
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -705,34 +915,65 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
   c->num_sms = prop.multiProcessorCount;
   c->Bmax = max_batch;
   c->steps = max_steps;
+  c->tp_rank = tp_rank;
+  c->tp_size = tp_size;
+  c->Hl = H / tp_size; c->Dl = c->Hl * hs; c->Fl = F / tp_size; c->Vl = V / tp_size;
   c->uploaded.assign((size_t)L2B_T_COUNT * L, 0);
   c->n_run.assign(max_batch, 0);
 
   int rc = 0;
 #define TRY(x) if (!rc) rc = (x)
   const size_t sD = D, sF = F, sL = L, sV = V, sS = S, sB = max_batch;
+  const size_t sDl = c->Dl, sFl = c->Fl, sVl = c->Vl;   // == full sizes when tp_size == 1
   TRY(dev_alloc(c, &c->tok_emb, sV * sD, false));
   TRY(dev_alloc(c, &c->rms_att, sL * sD, false));
-  TRY(dev_alloc(c, &c->wqkv, sL * 3 * sD * sD, false));
-  TRY(dev_alloc(c, &c->wo, sL * sD * sD, false));
+  TRY(dev_alloc(c, &c->wqkv, sL * 3 * sDl * sD, false));
+  TRY(dev_alloc(c, &c->wo, sL * sDl * sD, false));
   TRY(dev_alloc(c, &c->rms_ffn, sL * sD, false));
-  TRY(dev_alloc(c, &c->w13, sL * 2 * sF * sD, false));
-  TRY(dev_alloc(c, &c->w2, sL * sD * sF, false));
+  TRY(dev_alloc(c, &c->w13, sL * 2 * sFl * sD, false));
+  TRY(dev_alloc(c, &c->w2, sL * sDl * sF, false));
   TRY(dev_alloc(c, &c->rms_final, sD, false));
   TRY(dev_alloc(c, &c->fcr, sS * (hs / 2), false));
   TRY(dev_alloc(c, &c->fci, sS * (hs / 2), false));
   if (c->shared_cls) {
-    c->wcls = c->tok_emb;  // llama2.ts:127
+    c->wcls = c->tok_emb + (size_t)tp_rank * sVl * sD;  // llama2.ts:127 (this rank's rows)
   } else {
-    TRY(dev_alloc(c, &c->wcls, sV * sD, false));
+    TRY(dev_alloc(c, &c->wcls, sVl * sD, false));
   }
-  c->weight_bytes = 4 * (sL * (4 * sD * sD + 3 * sD * sF + 2 * sD) + sD + sV * sD);
-  TRY(dev_alloc(c, &c->x, sB * sD, true));
-  TRY(dev_alloc(c, &c->xb, sB * sD, true));
-  TRY(dev_alloc(c, &c->q, sB * sD, true));
-  TRY(dev_alloc(c, &c->hb, sB * sF, true));
-  TRY(dev_alloc(c, &c->logits, sB * sV, true));
-  const size_t kv = sL * sB * sD * (size_t)max_steps;
+  c->weight_bytes = 4 * (sL * (4 * sDl * sD + 3 * sD * sFl + 2 * sD) + sD + sVl * sD);
+  if (tp_size == 1) {
+    TRY(dev_alloc(c, &c->x, sB * sD, true));
+    TRY(dev_alloc(c, &c->xb, sB * sD, true));
+    TRY(dev_alloc(c, &c->hb, sB * sF, true));
+    TRY(dev_alloc(c, &c->logits, sB * sV, true));
+  } else {
+    // every vector that is gathered from all ranks lives in ONE allocation that the peers map
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const int n_ex = 4 * L + 1;
+    c->off_x = 0;
+    c->off_xb = al(c->off_x + sD * 4);
+    c->off_hb = al(c->off_xb + sD * 4);
+    c->off_logits = al(c->off_hb + sF * 4);
+    c->off_amv = al(c->off_logits + sV * 4);
+    c->off_ami = al(c->off_amv + kMaxTp * 4);
+    c->off_flags = al(c->off_ami + kMaxTp * 4);
+    c->xchg_bytes = al(c->off_flags + (size_t)n_ex * kMaxTp * 4);
+    TRY(dev_alloc(c, &c->xchg, c->xchg_bytes, true));
+    if (!rc) {
+      c->x = (float*)(c->xchg + c->off_x);
+      c->xb = (float*)(c->xchg + c->off_xb);
+      c->hb = (float*)(c->xchg + c->off_hb);
+      c->logits = (float*)(c->xchg + c->off_logits);
+      c->peer[tp_rank] = c->xchg;
+    }
+    int* tpw = nullptr;
+    TRY(dev_alloc(c, &tpw, 8, true));
+    c->tp_epoch = tpw;
+    c->tp_ticket = tpw ? tpw + 1 : nullptr;
+    c->tp_err = tpw ? tpw + 2 : nullptr;
+  }
+  TRY(dev_alloc(c, &c->q, sB * sDl, true));
+  const size_t kv = sL * sB * sDl * (size_t)max_steps;
   TRY(dev_alloc(c, &c->kc, kv, true));
   TRY(dev_alloc(c, &c->vc, kv, true));
   TRY(dev_alloc(c, &c->d_ctl, CTL_HDR + 2 * sB, true));
@@ -757,6 +998,7 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     cudaError_t e2 = cudaMallocHost((void**)&c->h_ctl, sizeof(int) * (CTL_HDR + 2 * sB));
     if (e2 == cudaSuccess) e2 = cudaMallocHost((void**)&c->h_logits, sizeof(float) * sB * sV);
     if (e2 == cudaSuccess) e2 = cudaMallocHost((void**)&c->h_out, sizeof(int) * (size_t)max_steps * sB);
+    if (e2 == cudaSuccess) e2 = cudaMallocHost((void**)&c->h_err, sizeof(int));
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev1);
@@ -792,6 +1034,14 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   drop_graphs(c);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  if (c->tp_size > 1) {
+    for (int g = 0; g < c->tp_size; ++g)
+      if (g != c->tp_rank && c->peer[g]) cudaIpcCloseMemHandle(c->peer[g]);
+    if (c->xchg) cudaFree(c->xchg);
+    if (c->tp_epoch) cudaFree(c->tp_epoch);
+    c->x = c->xb = c->hb = c->logits = nullptr;
+  }
+  if (c->h_err) cudaFreeHost(c->h_err);
   float* fl[] = {c->tok_emb, c->rms_att, c->wqkv, c->wo, c->rms_ffn, c->w13, c->w2, c->rms_final,
                  c->fcr, c->fci, c->shared_cls ? nullptr : c->wcls, c->x, c->xb, c->q, c->hb,
                  c->logits, c->kc, c->vc, c->blk_val, c->XhD, c->XlD, c->XhF, c->XlF, c->P};
@@ -819,26 +1069,35 @@ L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float
   if (layer < 0 || layer >= (layered ? c->L : 1))
     return fail(c, L2B_EINVAL, "layer %d out of range for tensor %d", layer, tensor_id);
   CU(c, cudaSetDevice(c->device));
-  size_t expect = 0;
+  // Row-sharded tensors keep rows [rank*slice, (rank+1)*slice) of the FULL tensor the caller
+  // passes (slice == all rows when tp_size == 1): `src_off` floats are skipped, `copy` copied.
+  const size_t Dl = c->Dl, Fl = c->Fl, Vl = c->Vl, r = c->tp_rank;
+  size_t expect = 0, src_off = 0, copy = 0, w13_rows = 0;
   float* dst = nullptr;
   switch (tensor_id) {
-    case L2B_T_TOKEN_EMBEDDING_TABLE: expect = V * D; dst = c->tok_emb; break;
-    case L2B_T_RMS_ATT_WEIGHT: expect = D; dst = c->rms_att + layer * D; break;
-    case L2B_T_WQ: expect = D * D; dst = c->wqkv + (size_t)layer * 3 * D * D; break;
-    case L2B_T_WK: expect = D * D; dst = c->wqkv + (size_t)layer * 3 * D * D + D * D; break;
-    case L2B_T_WV: expect = D * D; dst = c->wqkv + (size_t)layer * 3 * D * D + 2 * D * D; break;
-    case L2B_T_WO: expect = D * D; dst = c->wo + (size_t)layer * D * D; break;
-    case L2B_T_RMS_FFN_WEIGHT: expect = D; dst = c->rms_ffn + layer * D; break;
-    case L2B_T_W1: expect = F * D; dst = c->w13 + (size_t)layer * 2 * F * D; break;
-    case L2B_T_W3: expect = F * D; dst = c->w13 + (size_t)layer * 2 * F * D + D; break;
-    case L2B_T_W2: expect = D * F; dst = c->w2 + (size_t)layer * D * F; break;
-    case L2B_T_RMS_FINAL_WEIGHT: expect = D; dst = c->rms_final; break;
-    case L2B_T_FREQ_CIS_REAL: expect = S * hs2; dst = c->fcr; break;
-    case L2B_T_FREQ_CIS_IMAG: expect = S * hs2; dst = c->fci; break;
+    case L2B_T_TOKEN_EMBEDDING_TABLE: expect = copy = V * D; dst = c->tok_emb; break;
+    case L2B_T_RMS_ATT_WEIGHT: expect = copy = D; dst = c->rms_att + layer * D; break;
+    case L2B_T_WQ:
+    case L2B_T_WK:
+    case L2B_T_WV:
+      expect = D * D; src_off = r * Dl * D; copy = Dl * D;
+      dst = c->wqkv + (size_t)layer * 3 * Dl * D + (size_t)(tensor_id - L2B_T_WQ) * Dl * D;
+      break;
+    case L2B_T_WO: expect = D * D; src_off = r * Dl * D; copy = Dl * D; dst = c->wo + (size_t)layer * Dl * D; break;
+    case L2B_T_RMS_FFN_WEIGHT: expect = copy = D; dst = c->rms_ffn + layer * D; break;
+    case L2B_T_W1:
+    case L2B_T_W3:
+      expect = F * D; src_off = r * Fl * D; w13_rows = Fl;
+      dst = c->w13 + (size_t)layer * 2 * Fl * D + (tensor_id == L2B_T_W3 ? D : 0);
+      break;
+    case L2B_T_W2: expect = D * F; src_off = r * Dl * F; copy = Dl * F; dst = c->w2 + (size_t)layer * Dl * F; break;
+    case L2B_T_RMS_FINAL_WEIGHT: expect = copy = D; dst = c->rms_final; break;
+    case L2B_T_FREQ_CIS_REAL: expect = copy = S * hs2; dst = c->fcr; break;
+    case L2B_T_FREQ_CIS_IMAG: expect = copy = S * hs2; dst = c->fci; break;
     case L2B_T_WCLS:
       if (c->shared_cls)
         return fail(c, L2B_ESTATE, "shared classifier: wcls aliases the embedding table (llama2.ts:127)");
-      expect = V * D; dst = c->wcls; break;
+      expect = V * D; src_off = r * Vl * D; copy = Vl * D; dst = c->wcls; break;
   }
   if (n_floats != expect)
     return fail(c, L2B_EINVAL, "tensor %d expects %zu floats, got %llu", tensor_id, expect,
@@ -847,10 +1106,10 @@ L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float
   CU(c, cudaStreamSynchronize(c->stream));
   if (tensor_id == L2B_T_W1 || tensor_id == L2B_T_W3) {
     // interleave rows: device row 2i = w1 row i, 2i+1 = w3 row i (pairs feed SwiGLU)
-    CU(c, cudaMemcpy2DAsync(dst, 2 * D * sizeof(float), host, D * sizeof(float), D * sizeof(float), F,
-                            cudaMemcpyDefault, c->stream));
+    CU(c, cudaMemcpy2DAsync(dst, 2 * D * sizeof(float), host + src_off, D * sizeof(float), D * sizeof(float),
+                            w13_rows, cudaMemcpyDefault, c->stream));
   } else {
-    CU(c, cudaMemcpyAsync(dst, host, expect * sizeof(float), cudaMemcpyDefault, c->stream));
+    CU(c, cudaMemcpyAsync(dst, host + src_off, copy * sizeof(float), cudaMemcpyDefault, c->stream));
   }
   // the copy runs on the ctx stream (device sources are asynchronous otherwise): the
   // caller may free `host` on return and the next step sees the new contents
@@ -981,6 +1240,8 @@ L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer
   if (!c) return L2B_EINVAL;
   if (!out) return fail(c, L2B_EINVAL, "null out");
   if (seq < 0 || seq >= c->Bmax) return fail(c, L2B_EINVAL, "seq %d", seq);
+  if (c->tp_size > 1 && (which == L2B_S_KEY_ROW || which == L2B_S_VALUE_ROW || which == L2B_S_Q))
+    return fail(c, L2B_ESTATE, "KV/q taps are per-rank slices in tensor-parallel mode");
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->stream));
   const size_t D = c->D;
@@ -1017,7 +1278,7 @@ L2B_API int l2b_reset(l2b_ctx* c) {
   if (!c) return L2B_EINVAL;
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->stream));
-  const size_t kv = (size_t)c->L * c->Bmax * c->D * (size_t)c->steps;
+  const size_t kv = (size_t)c->L * c->Bmax * c->Dl * (size_t)c->steps;
   CU(c, cudaMemsetAsync(c->kc, 0, kv * sizeof(float), c->stream));
   CU(c, cudaMemsetAsync(c->vc, 0, kv * sizeof(float), c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -1061,14 +1322,35 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
 }
 
 L2B_API int64_t l2b_tp_export(l2b_ctx* c, void* blob, uint64_t cap) {
-  (void)blob;
-  (void)cap;
-  return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
+  if (!c) return L2B_EINVAL;
+  if (c->tp_size <= 1) return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
+  if (!blob || cap < sizeof(cudaIpcMemHandle_t)) return fail(c, L2B_EINVAL, "blob needs %zu bytes", sizeof(cudaIpcMemHandle_t));
+  CU(c, cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CU(c, cudaIpcGetMemHandle(&h, c->xchg));
+  memcpy(blob, &h, sizeof h);
+  return (int64_t)sizeof h;
 }
 
 L2B_API int l2b_tp_connect(l2b_ctx* c, const void* blobs, uint64_t blob_bytes, int32_t n_ranks) {
-  (void)blobs;
-  (void)blob_bytes;
-  (void)n_ranks;
-  return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
+  if (!c) return L2B_EINVAL;
+  if (c->tp_size <= 1) return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
+  if (!blobs || n_ranks != c->tp_size || blob_bytes < sizeof(cudaIpcMemHandle_t))
+    return fail(c, L2B_EINVAL, "expected %d blobs of >= %zu bytes", c->tp_size, sizeof(cudaIpcMemHandle_t));
+  CU(c, cudaSetDevice(c->device));
+  for (int g = 0; g < c->tp_size; ++g) {
+    if (g == c->tp_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const unsigned char*)blobs + (size_t)g * blob_bytes, sizeof h);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, L2B_ECOMM, "cudaIpcOpenMemHandle(rank %d): %s", g, cudaGetErrorString(e));
+    }
+    c->peer[g] = (unsigned char*)p;
+  }
+  c->tp_connected = true;
+  drop_graphs(c);
+  return L2B_OK;
 }

@@ -67,3 +67,14 @@ class ShardedBatch:
             tok = np.asarray(self.step_fn(tok, np.full(self.count, s, np.int32)), dtype=np.int32)
             out[s] = gather_tokens(tok, self.n, self.device)
         return out
+
+
+def connect_tp(ctx):
+    """Exchange the ranks' handle blobs over the initialised process group and wire the
+    tensor-parallel context (l2b_tp_export -> all_gather -> l2b_tp_connect)."""
+    d = _dist()
+    assert d is not None and d.get_world_size() == ctx.tp_size
+    blobs = [None] * ctx.tp_size
+    d.all_gather_object(blobs, ctx.tp_export())
+    ctx.tp_connect(blobs)
+    d.barrier()

@@ -136,9 +136,12 @@ class Model:
         self.seq_len = int(hdr[6])
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().l2ref_destroy(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None) and _lib is not None:
+                _lib.l2ref_destroy(self.h)
+                self.h = None
+        except Exception:          # interpreter shutdown
+            pass
 
     def forward(self, token, pos):
         """transformer(token,pos) -> copy of s.logits (llama2.ts:205-303)."""

@@ -1,0 +1,87 @@
+"""Row-sharded tensor-parallel decode (one process per GPU, in-kernel NVLink exchange):
+every rank's logits must equal the single-GPU library's bit for bit (row sharding keeps every
+output's summation order) and match the oracle within tolerance.  Needs >= 2 GPUs."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+import torch, torch.distributed as dist
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+import llama2_ts_b200 as pkg
+from oracle import l2ref
+arch, steps = %(arch)r, %(steps)d
+hdr = pkg.synth.header(arch)
+_, blob = pkg.synth.checkpoint_blob(hdr, seed=41, std=0.04)
+V = abs(hdr[5])
+ctx = pkg.Context(hdr, device=rank, max_steps=steps, tp_rank=rank, tp_size=world)
+pkg.synth.upload_blob(ctx, hdr, blob)          # full tensors; the library keeps this rank's rows
+pkg.dist.connect_tp(ctx)
+toks = np.concatenate([[1], pkg.synth.teacher_tokens(steps - 1, V, 41)])
+single = pkg.Context(hdr, device=rank, max_steps=steps)
+pkg.synth.upload_blob(single, hdr, blob)
+ref = l2ref.Model(hdr, blob)
+l2ref.set_threads(4)
+worst, ok_bits = 0.0, True
+for pos in range(steps):
+    got = ctx.forward(int(toks[pos]), pos)
+    one = single.forward(int(toks[pos]), pos)
+    want = ref.forward(int(toks[pos]), pos)
+    assert np.allclose(got, want, rtol=1e-3, atol=1e-4), (rank, pos, np.abs(got - want).max())
+    ok_bits = ok_bits and np.array_equal(got, one)
+    worst = max(worst, float(np.abs(got - want).max()))
+    assert ctx.forward_argmax(int(toks[pos]), pos) == l2ref.argmax(want)
+assert ok_bits, "tensor-parallel logits differ from the single-GPU logits"
+# device-resident greedy loop across the ranks
+ctx.reset(); single.reset()
+forced = np.full(steps, -1, np.int32); forced[:3] = toks[1:4]
+a = ctx.generate_greedy([1], [0], steps, forced)[:, 0]
+b = single.generate_greedy([1], [0], steps, forced)[:, 0]
+assert np.array_equal(a, b), (rank, a, b)
+ms_tp, ms_one = ctx.last_device_ms() / steps, single.last_device_ms() / steps
+dist.barrier()
+print("rank %%d ok: max|dlogit| %%.3g, bit-identical to 1 GPU, %%.3f ms/step (1 GPU %%.3f)" %% (rank, worst, ms_tp, ms_one))
+ctx.close(); single.close()
+dist.destroy_process_group()
+'''
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("arch,steps", [("small", 24), ("wide", 20)])
+def test_tensor_parallel_matches_single_gpu(arch, steps, tmp_path):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    world = 4 if (n >= 4 and arch == "wide") else 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "tp_worker.py"
+    script.write_text(WORKER % {"root": ROOT, "port": port, "arch": arch, "steps": steps})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world)]) for r in range(world)]
+    codes = []
+    for p in procs:
+        try:
+            codes.append(p.wait(timeout=300))
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    assert codes == [0] * world, codes
