@@ -202,14 +202,19 @@ def cpu_sample(oracle, hdr, blob, threads, budget_s, max_tokens, warm=0):
     return n / dt, n, dt
 
 
-def run_workload(pkg, name, device, steps, warmup, seed, B=1, keep_host=False):
+def run_workload(pkg, name, device, steps, warmup, seed, B=1, keep_host=False, tp=None):
     """Builds the named architecture on this rank's GPU (random-init weights generated on the
     device) with B independent sequences; returns (state, loop_device)."""
     hdr = pkg.synth.header(name)
     S = hdr[6]
     rows = min(S, warmup + steps)
-    ctx = pkg.Context(hdr, device=device, max_batch=B, max_steps=rows)
+    if tp:
+        ctx = pkg.Context(hdr, device=device, max_steps=rows, tp_rank=tp[0], tp_size=tp[1])
+    else:
+        ctx = pkg.Context(hdr, device=device, max_batch=B, max_steps=rows)
     blob = build_weights_on_gpu(pkg, ctx, hdr, seed, "cuda:%d" % device, keep_host)
+    if tp:
+        pkg.dist.connect_tp(ctx)
     out = {"hdr": hdr, "ctx": ctx, "blob": blob, "rows": rows, "B": B}
     V = abs(hdr[5])
 
@@ -244,6 +249,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0,
                     help="GLOBAL number of independent sequences, partitioned over the ranks "
                          "(strong scaling); 0 = one sequence per GPU (weak scaling, the default)")
+    ap.add_argument("--tp", action="store_true",
+                    help="all ranks form ONE tensor-parallel group decoding a single sequence "
+                         "(row-sharded projections + in-kernel NVLink exchange; strong scaling)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true")
@@ -267,6 +275,10 @@ def main():
         scaling = "strong"
         par = "%d independent sequences partitioned over %d GPU(s), %d per GPU (weights replicated, " \
               "no data-path collective)" % (args.batch, world, B)
+    elif args.tp and world > 1:
+        B, scaling = 1, "strong"
+        par = "tensor parallel tp%d: rows of every projection sharded over the ranks, slices exchanged " \
+              "by peer stores over NVLink inside the kernels (4 all-gathers per layer)" % world
     else:
         B, scaling = 1, "weak"
         par = "independent sequences per GPU (weights replicated, no collective)"
@@ -335,8 +347,9 @@ def main():
     if want_cpu and not host_mem_ok(4 * pkg.synth.weight_floats(hdr)):
         want_cpu, cpu_skip = False, "host memory too small for a %.1f GB checkpoint copy" % (
             4e-9 * pkg.synth.weight_floats(hdr))
+    tp = (rank, world) if (args.tp and world > 1) else None
     st, loop_device = run_workload(pkg, args.workload, local_rank, args.steps, args.warmup,
-                                   args.seed + rank, B=B, keep_host=want_cpu)
+                                   args.seed + (0 if tp else rank), B=B, keep_host=want_cpu, tp=tp)
     ctx, rows = st["ctx"], st["rows"]
     for kv in args.opt:
         k, v = kv.split("=")
@@ -399,6 +412,8 @@ def main():
               K.K_GEMM_CLS: 4 * V * D + act * (D + V), K.K_BATCH_EPI: 0}
     kflops = {K.K_GEMM_QKV: 2.0 * 3 * D * D * B, K.K_GEMM_WO: 2.0 * D * D * B,
               K.K_GEMM_W13: 2.0 * 2 * F * D * B, K.K_GEMM_W2: 2.0 * D * F * B, K.K_GEMM_CLS: 2.0 * V * D * B}
+    if tp:   # every rank streams 1/world of each weight matrix
+        kbytes = {k: v / world for k, v in kbytes.items()}
     peak, peak_src = peaks()
     tpeak = tensor_peak()
     per_kernel = {}
@@ -427,10 +442,10 @@ def main():
         if tf / tpeak > hbm_rate / peak:
             roof.update({"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak})
 
-    n_tok = args.steps * world * B
+    n_tok = args.steps * (1 if tp else world) * B
     value = n_tok / (ms * 1e-3)
     mean_pos = (pos + (args.steps - 1) / 2.0) % rows
-    sbytes = pkg.synth.step_bytes(hdr, mean_pos, B=B)
+    sbytes = pkg.synth.step_bytes(hdr, mean_pos, B=B) / (world if tp else 1)   # per GPU
     step_s = ms / args.steps * 1e-3
     roof["step"] = {"bytes_per_step": sbytes, "achieved": sbytes / step_s / 1e9,
                     "frac": sbytes / step_s / 1e9 / peak,

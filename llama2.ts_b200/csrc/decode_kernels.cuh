@@ -46,14 +46,19 @@ constexpr int kMaxNB = 8;      // sequences sharing one weight pass
 
 // Tensor-parallel exchange (row-sharded projections).  Every rank
 // holds replicas of the gathered vectors (x, xb, hb, logits); a kernel's epilogue stores its
-// slice straight into EVERY peer's replica over NVLink (peer-mapped pointers) and the last
-// CTA publishes a sequence number to every peer's flag word; the consumer kernel spins on its
-// local flags before it reads the gathered vector.  No NCCL launch on the critical path.
+// slice straight into EVERY peer's replica over NVLink (peer-mapped pointers).  The
+// per-layer vectors use a flag-in-data ("LL") layout: each element is an 8-byte
+// {value, sequence number} word written with ONE store, and the consumer kernel spins on
+// the sequence number of exactly the elements it loads -- no fence, no ticket, no separate
+// flag write on the critical path (a first version with __threadfence_system + last-CTA
+// flags cost ~16 us per exchange on 2 B200s; there are 4 exchanges per layer).  Only the
+// classifier -> finalize hand-off (once per step, plain logits for the host) keeps the
+// fence + flag protocol.  No NCCL launch anywhere on the path.
 constexpr int kMaxTp = 8;
 struct TpParams {
   int rank, size;
   const int* epoch;            // device word: sequence base of the current step
-  const int* wait_flags;       // local flags[e_in][0..size) to wait on, or nullptr
+  int ll_in;                   // 1: the input vector is an LL replica tagged with sequence wait_idx
   int wait_idx;                // e_in
   int out_idx;                 // e_out
   int out_off;                 // rank * slice: where this rank's results sit in the gathered vector
@@ -76,6 +81,39 @@ __device__ __forceinline__ void tp_wait_flag(const int* f, int seq, int* err) {
       break;
     }
   }
+}
+
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_sys_u4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void st_sys_u2(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+// elements 4j..4j+3 of an LL replica; check: spin until all four carry sequence `seq`
+__device__ __forceinline__ float4 ll_load4(const void* base, int j, bool check, int seq, int* err) {
+  const uint4* b4 = reinterpret_cast<const uint4*>(base) + 2 * (size_t)j;
+  uint4 a = ld_volatile_u4(b4), b = ld_volatile_u4(b4 + 1);
+  if (check) {
+    const long long t0 = clock64();
+    while (!((int)a.y == seq && (int)a.w == seq && (int)b.y == seq && (int)b.w == seq)) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(err, 1);
+        break;
+      }
+      a = ld_volatile_u4(b4);
+      b = ld_volatile_u4(b4 + 1);
+    }
+  }
+  return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
 
 struct GemvParams {
@@ -228,13 +266,9 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
   // ---- everything below may depend on the previous kernel ----
   griddep_wait();
   int tp_seq = 0;
-  if (TP) {
-    tp_seq = ld_act_i32(p.tp.epoch) + 1;
-    if (p.tp.wait_flags != nullptr) {  // the gathered input must have arrived from every rank
-      if ((int)threadIdx.x < p.tp.size) tp_wait_flag(p.tp.wait_flags + threadIdx.x, tp_seq + p.tp.wait_idx, p.tp.err);
-      __syncthreads();
-    }
-  }
+  if (TP) tp_seq = ld_act_i32(p.tp.epoch) + 1;
+  const bool ll_in = TP && p.tp.ll_in != 0;   // input is an LL replica: spin on its sequence tags
+  const int seq_in = tp_seq + p.tp.wait_idx;
 
   // prologue: build the activation vector(s) in shared memory
   {
@@ -250,7 +284,7 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
         const float4* src4 = reinterpret_cast<const float4*>(src);
         const bool write_x = (p.tok_emb != nullptr) && blockIdx.x == 0;
         for (int j = threadIdx.x; j < n4; j += THREADS) {
-          const float4 v = ld_act4(src4 + j);
+          const float4 v = ll_in ? ll_load4(p.vin, j, true, seq_in, p.tp.err) : ld_act4(src4 + j);
           if (PRO == PRO_COPY) {
             XV::store(xs, n4, j, v);
           } else {
@@ -258,7 +292,15 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
             ss[s] += (double)v.x * (double)v.x + (double)v.y * (double)v.y +
                      (double)v.z * (double)v.z + (double)v.w * (double)v.w;
           }
-          if (write_x) reinterpret_cast<float4*>(p.x + (size_t)b * p.xdim)[j] = v;  // :211
+          if (write_x) {  // x.set(embedding row), llama2.ts:211
+            if (TP) {
+              uint4* xl = reinterpret_cast<uint4*>(p.x) + 2 * (size_t)j;
+              xl[0] = make_uint4(__float_as_uint(v.x), 0u, __float_as_uint(v.y), 0u);
+              xl[1] = make_uint4(__float_as_uint(v.z), 0u, __float_as_uint(v.w), 0u);
+            } else {
+              reinterpret_cast<float4*>(p.x + (size_t)b * p.xdim)[j] = v;
+            }
+          }
         }
       } else {
         for (int j = threadIdx.x; j < n4; j += THREADS) XV::store(xs, n4, j, f4_zero());
@@ -286,7 +328,7 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
           const float4* src4 = reinterpret_cast<const float4*>(src);
           const float4* rw4 = reinterpret_cast<const float4*>(p.rms_w);
           for (int j = threadIdx.x; j < n4; j += THREADS) {
-            const float4 v = ld_act4(src4 + j);  // L1/L2 hit: read a moment ago
+            const float4 v = ll_in ? ll_load4(p.vin, j, false, 0, nullptr) : ld_act4(src4 + j);  // L2 hit
             const float4 w = __ldg(rw4 + j);
             float4 o;  // o[j] = weight[j] * (ss * x[j]), stored as f32 (llama2.ts:177)
             o.x = (float)((double)w.x * (tot * (double)v.x));
@@ -397,13 +439,14 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
         } else if (EPI == EPI_RESID) {
           // accum(x, xb2), llama2.ts:168-170,273,295
           if (TP) {
-            const int gi = p.tp.out_off + r;  // index in the replicated residual stream
-            const float n0 = (float)((double)ld_act(p.x + gi) + (double)s0);
-            const float n1 = (float)((double)ld_act(p.x + gi + 1) + (double)s1);
-            for (int g = 0; g < p.tp.size; ++g) {
-              st_relaxed_sys_f32(p.tp.peer_out[g] + gi, n0);
-              st_relaxed_sys_f32(p.tp.peer_out[g] + gi + 1, n1);
-            }
+            const int gi = p.tp.out_off + r;  // index in the replicated residual stream (LL words)
+            const uint4 old = ld_volatile_u4(reinterpret_cast<const uint4*>(p.x) + (gi >> 1));
+            const float n0 = (float)((double)__uint_as_float(old.x) + (double)s0);
+            const float n1 = (float)((double)__uint_as_float(old.z) + (double)s1);
+            const uint32_t sq = (uint32_t)(tp_seq + p.tp.out_idx);
+            for (int g = 0; g < p.tp.size; ++g)
+              st_sys_u4(reinterpret_cast<uint4*>(p.tp.peer_out[g]) + (gi >> 1), __float_as_uint(n0), sq,
+                        __float_as_uint(n1), sq);
           } else {
             float* xr = p.x + (size_t)eb * p.xdim + r;
             xr[0] = (float)((double)xr[0] + (double)s0);
@@ -415,7 +458,9 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
           const float silu = (float)(hv * (1.0 / (1.0 + exp(-hv))));
           const float hv2 = (float)((double)silu * (double)s1);
           if (TP) {
-            for (int g = 0; g < p.tp.size; ++g) st_relaxed_sys_f32(p.tp.peer_out[g] + p.tp.out_off + pair, hv2);
+            const uint32_t sq = (uint32_t)(tp_seq + p.tp.out_idx);
+            for (int g = 0; g < p.tp.size; ++g)
+              st_sys_u2(reinterpret_cast<uint2*>(p.tp.peer_out[g]) + p.tp.out_off + pair, __float_as_uint(hv2), sq);
           } else {
             p.hb[(size_t)eb * p.hb_stride + pair] = hv2;
           }
@@ -440,23 +485,6 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
     pair = npair;
     jt = njt;
     cur = nxt;
-  }
-
-  if (TP && (EPI == EPI_RESID || EPI == EPI_SWIGLU)) {
-    // publish: every remote store of this CTA is ordered before its ticket; the last CTA
-    // raises this rank's flag on every peer
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int t = atomicAdd(p.tp.ticket, 1);
-      s_is_last = (t == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_is_last) {
-      __threadfence_system();
-      if ((int)threadIdx.x < p.tp.size) st_release_sys_i32(p.tp.peer_flags[threadIdx.x], tp_seq + p.tp.out_idx);
-      if (threadIdx.x == 0) *p.tp.ticket = 0;
-    }
   }
 
   if (EPI == EPI_LOGITS) {
@@ -585,8 +613,7 @@ struct AttnParams {
   int tp_size;
   const int* tp_epoch;     // device word: sequence base of the current step
   int tp_out_idx;          // exchange index of this all-gather
-  int* tp_ticket;          // local ticket counter
-  int* tp_peer_flags[kMaxTp];
+
   // batched tensor-core path: also emit the TF32 hi/lo split of the output (input of the wo GEMM)
   float* xh;
   float* xl;
@@ -796,24 +823,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
     if (p.tp_size <= 1) {
       p.xb[o] = s;
     } else {
-      for (int r = 0; r < p.tp_size; ++r) st_relaxed_sys_f32(p.peer_xb[r] + o, s);
-    }
-  }
-  if (p.tp_size > 1 && rank == 0) {
-    // all-gather publication: last (sequence, head) leader raises this rank's flag on every peer
-    __shared__ int s_last;
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      const int t = atomicAdd(p.tp_ticket, 1);
-      s_last = (t == (int)(gridDim.y * gridDim.z) - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence_system();
-      const int seq = ld_act_i32(p.tp_epoch) + 1 + p.tp_out_idx;
-      if (tid < p.tp_size) st_release_sys_i32(p.tp_peer_flags[tid], seq);
-      if (tid == 0) *p.tp_ticket = 0;
+      const uint32_t sq = (uint32_t)(ld_act_i32(p.tp_epoch) + 1 + p.tp_out_idx);
+      for (int r = 0; r < p.tp_size; ++r)
+        st_sys_u2(reinterpret_cast<uint2*>(p.peer_xb[r]) + o, __float_as_uint(s), sq);
     }
   }
   cluster_sync_all();  // keep every CTA's shared memory alive until rank 0 has read it

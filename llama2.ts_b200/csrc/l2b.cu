@@ -473,7 +473,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
     memset(&t, 0, sizeof t);
     t.rank = R; t.size = G;
     t.epoch = c->tp_epoch; t.ticket = c->tp_ticket; t.err = c->tp_err;
-    t.wait_flags = wait_e >= 0 ? flag_on(R, wait_e, 0) : nullptr;
+    t.ll_in = wait_e >= 0 ? 1 : 0;
     t.wait_idx = wait_e < 0 ? 0 : wait_e;
     t.out_idx = out_e < 0 ? 0 : out_e;
     t.out_off = out_off;
@@ -549,11 +549,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       a.tp_size = G;
       a.tp_epoch = c->tp_epoch;
       a.tp_out_idx = eA;
-      a.tp_ticket = c->tp_ticket;
-      for (int g = 0; g < G; ++g) {
-        a.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
-        a.tp_peer_flags[g] = flag_on(g, eA, R);
-      }
+      for (int g = 0; g < G; ++g) a.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
       const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
       int rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, Hl, 1), dim3(kAttnThreads), smem,
@@ -950,10 +946,10 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     // every vector that is gathered from all ranks lives in ONE allocation that the peers map
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const int n_ex = 4 * L + 1;
-    c->off_x = 0;
-    c->off_xb = al(c->off_x + sD * 4);
-    c->off_hb = al(c->off_xb + sD * 4);
-    c->off_logits = al(c->off_hb + sF * 4);
+    c->off_x = 0;                               // x, xb, hb: LL replicas, 8 bytes per element
+    c->off_xb = al(c->off_x + sD * 8);
+    c->off_hb = al(c->off_xb + sD * 8);
+    c->off_logits = al(c->off_hb + sF * 8);
     c->off_amv = al(c->off_logits + sV * 4);
     c->off_ami = al(c->off_amv + kMaxTp * 4);
     c->off_flags = al(c->off_ami + kMaxTp * 4);
@@ -1240,8 +1236,8 @@ L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer
   if (!c) return L2B_EINVAL;
   if (!out) return fail(c, L2B_EINVAL, "null out");
   if (seq < 0 || seq >= c->Bmax) return fail(c, L2B_EINVAL, "seq %d", seq);
-  if (c->tp_size > 1 && (which == L2B_S_KEY_ROW || which == L2B_S_VALUE_ROW || which == L2B_S_Q))
-    return fail(c, L2B_ESTATE, "KV/q taps are per-rank slices in tensor-parallel mode");
+  if (c->tp_size > 1 && which != L2B_S_LOGITS)
+    return fail(c, L2B_ESTATE, "only the logits tap exists in tensor-parallel mode (state is sharded / LL-tagged)");
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->stream));
   const size_t D = c->D;
