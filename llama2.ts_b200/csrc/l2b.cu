@@ -20,6 +20,7 @@
 #include "../../include/llama2_b200.h"
 #include "batch_gemm.cuh"
 #include "decode_kernels.cuh"
+#include "mega_kernel.cuh"
 
 #define L2B_API extern "C" __attribute__((visibility("default")))
 
@@ -40,6 +41,8 @@ struct Options {
   int tc_min_batch = 5;  // batches >= this run the tcgen05 GEMM path (0 = never)
   int tc_splits = 0;     // 0 = auto k-split per GEMM
   int tc_rewrite_hi = 0; // see GemmParams::rewrite_hi
+  int mega = 0;          // batch-1: whole step (and greedy loop) as one persistent cooperative kernel
+                         // (experiment, opt-in: measured slower than graph+PDL so far)
 };
 
 }  // namespace
@@ -73,6 +76,7 @@ struct l2b_ctx {
   float* blk_val = nullptr;
   int* blk_idx = nullptr;
   int *d_forced = nullptr, *d_out = nullptr;
+  unsigned* d_bar = nullptr;  // grid barrier words of the persistent kernel
   // batched tensor-core path: pre-split activations [256*groups][D or F], partial sums
   float *XhD = nullptr, *XlD = nullptr, *XhF = nullptr, *XlF = nullptr, *P = nullptr;
   int Bpad = 0, Smax = 8;
@@ -753,10 +757,68 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   return 0;
 }
 
+// Batch-1 persistent kernel: one cooperative launch runs n_steps decode steps.
+int launch_mega(l2b_ctx* c, int n_steps, cudaStream_t st) {
+  MegaParams m;
+  memset(&m, 0, sizeof m);
+  m.D = c->D; m.F = c->F; m.L = c->L; m.H = c->H; m.hs = c->hs; m.V = c->V; m.steps = c->steps;
+  m.tok_emb = c->tok_emb; m.rms_att = c->rms_att; m.wqkv = c->wqkv; m.wo = c->wo; m.rms_ffn = c->rms_ffn;
+  m.w13 = c->w13; m.w2 = c->w2; m.rms_final = c->rms_final; m.fcr = c->fcr; m.fci = c->fci; m.wcls = c->wcls;
+  m.x = c->x; m.xb = c->xb; m.q = c->q; m.hb = c->hb; m.logits = c->logits; m.kc = c->kc; m.vc = c->vc;
+  m.kv_layer = (long long)c->H * c->steps * c->hs * c->Bmax;
+  m.ctl = c->d_ctl; m.next = c->d_dev + 1; m.forced = c->d_forced; m.out_tokens = c->d_out;
+  m.blk_val = c->blk_val; m.blk_idx = c->blk_idx; m.bar = c->d_bar;
+  m.n_steps = n_steps;
+  int ef = c->opt.evict_first;
+  if (ef < 0) ef = c->weight_bytes > (size_t)100 * 1024 * 1024;
+  m.evict_first = ef;
+  const int nmax = c->D > c->F ? c->D : c->F;
+  size_t smem = (size_t)nmax * 8;
+  const size_t attn = ((size_t)((c->steps + 3) & ~3) + (size_t)kMegaWarps * kAttnMaxHs) * 4;
+  if (attn > smem) smem = attn;
+  smem += (size_t)kMegaWarps * kMU * 2 * 32 * 16;  // prefetch stage
+  const void* fn = (const void*)mega_decode_kernel;
+  if (!c->smem_set.count(fn)) {
+    cudaFuncAttributes fa;
+    CU(c, cudaFuncGetAttributes(&fa, fn));
+    CU(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024 - (int)fa.sharedSizeBytes));
+    c->smem_set.insert(fn);
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(c->num_sms);
+  cfg.blockDim = dim3(kMegaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  memset(at, 0, sizeof at);
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  void* args[] = {&m};
+  CU(c, cudaLaunchKernelExC(&cfg, fn, args));
+  c->launch_counter++;
+  return 0;
+}
+
+bool use_mega(const l2b_ctx* c, int B) {
+  return c->opt.mega && B == 1 && c->Bmax == 1 && c->tp_size == 1 && !c->profiling && c->H <= c->num_sms;
+}
+
 // Runs `n_steps` decode steps for B sequences, graph-launched when enabled.
 // Events ev0/ev1 bracket the device work on the ctx stream.
 int run_steps(l2b_ctx* c, int B, int n_steps) {
   const int64_t l0 = c->launch_counter;
+  if (use_mega(c, B)) {
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    int rc = launch_mega(c, n_steps, c->stream);
+    if (rc) return rc;
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    c->last_launches = c->launch_counter - l0;
+    return 0;
+  }
   const bool use_graph = c->opt.graph != 0 && !c->profiling;
   cudaGraphExec_t ge = nullptr;
   if (use_graph) {
@@ -987,6 +1049,7 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     TRY(dev_alloc(c, &c->XlF, (size_t)c->Bpad * sF + 64, true));
     TRY(dev_alloc(c, &c->P, (size_t)c->Smax * sB * Mmax, false));
   }
+  TRY(dev_alloc(c, &c->d_bar, 4, true));
   TRY(dev_alloc(c, &c->d_forced, (size_t)max_steps * sB, true));
   TRY(dev_alloc(c, &c->d_out, (size_t)max_steps * sB, true));
 #undef TRY
@@ -1043,7 +1106,7 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
                  c->logits, c->kc, c->vc, c->blk_val, c->XhD, c->XlD, c->XhF, c->XlF, c->P};
   for (float* p : fl)
     if (p) cudaFree(p);
-  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out};
+  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar};
   for (int* p : il)
     if (p) cudaFree(p);
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -1304,6 +1367,8 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.evict_first = v < 0 ? -1 : (v != 0);
   } else if (k == "tc_min_batch") {
     o.tc_min_batch = v < 0 ? 0 : v;
+  } else if (k == "mega") {
+    o.mega = v != 0;
   } else if (k == "tc_rewrite_hi") {
     o.tc_rewrite_hi = v != 0;
   } else if (k == "tc_splits") {

@@ -133,6 +133,11 @@ def test_variants_agree(pkg, oracle):
         ctx.reset()
         return [ctx.forward(int(t), p) for p, t in enumerate(toks)]
 
+    ctx.set_option("mega", 1)         # opt-in experiment: persistent cooperative kernel
+    mega = run()
+    for p in range(len(toks)):
+        assert close(mega[p], want[p]), ("mega", p)
+    ctx.set_option("mega", 0)         # default: one kernel per fused op, CUDA graph + PDL
     base = run()
     for opts in ({"graph": 0}, {"pdl": 0}, {"graph": 0, "pdl": 0}, {"threads": 256},
                  {"threads": 256, "ctas_per_sm": 2}, {"attn_cluster": 1}, {"attn_cluster": 2},
