@@ -468,6 +468,20 @@ def main():
         "clocks": clk,
     }
 
+    if B == 1 and not tp:
+        # the prompt as one batched tensor-core pass vs one decode step per token
+        n_pf = min(256, rows)
+        pf_toks = pkg.synth.teacher_tokens(n_pf, V, 5)
+        ctx.reset()
+        ctx.prefill(pf_toks, 0, want_logits=False)          # warm-up (allocates the scratch)
+        ctx.reset()
+        ctx.prefill(pf_toks, 0, want_logits=False)
+        pf_ms = ctx.last_device_ms()
+        line["prefill"] = {"prompt_tokens": int(n_pf), "device_ms": pf_ms,
+                           "tokens_per_s": n_pf / (pf_ms * 1e-3),
+                           "speedup_vs_token_by_token": (ms / args.steps) * n_pf / pf_ms,
+                           "note": "l2b_prefill: all prompt positions in one 3xTF32 tcgen05 pass "
+                                   "(the reference runs one transformer() call per prompt token)"}
     if want_cpu:
         oracle.build()
         tps, n, dt = cpu_sample(oracle, hdr, st["blob"], 1, 20.0, 4)

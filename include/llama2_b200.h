@@ -107,6 +107,16 @@ int l2b_forward_argmax(l2b_ctx* ctx, int32_t token, int32_t pos, int32_t* next_o
 int l2b_forward_batch(l2b_ctx* ctx, int32_t B, const int32_t* tokens, const int32_t* pos,
                       float* logits_out, int32_t* argmax_out);
 
+/* Prompt prefill.  The reference feeds the prompt one token
+ * at a time through transformer() and throws the logits away (llama2.ts:465-474).  This call
+ * has the same effect on sequence `seq` as n_tokens successive l2b_forward(tokens[i],
+ * pos0 + i) calls -- KV rows pos0..pos0+n_tokens-1 are written -- but runs all positions in
+ * ONE pass over the weights on the tensor cores (causal attention inside the batch).
+ * logits_out (vocab floats) / argmax_out receive the LAST position's logits / argmax; either
+ * may be NULL.  Numerics: the 3xTF32 path (within the 1e-4 / 1e-3 tolerance, not bit-exact). */
+int l2b_prefill(l2b_ctx* ctx, int32_t seq, int32_t n_tokens, const int32_t* tokens, int32_t pos0,
+                float* logits_out, int32_t* argmax_out);
+
 /* The greedy generate loop of llama2.ts:465-508 kept on the device: starting
  * from `token` at `pos`, runs `n_steps` steps; step i feeds forced[i] when
  * forced != NULL and forced[i] >= 0 (prompt forcing, llama2.ts:471-473), else

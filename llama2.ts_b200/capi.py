@@ -56,6 +56,7 @@ _SIGNATURES = {
     "l2b_forward_argmax": (C.c_int, [_p, _i32, _i32, C.POINTER(_i32)]),
     "l2b_forward_batch": (C.c_int, [_p, _i32, _p, _p, _p, _p]),
     "l2b_generate_greedy": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _p]),
+    "l2b_prefill": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, C.POINTER(_i32)]),
     "l2b_last_device_ms": (_f32, [_p]),
     "l2b_last_launches": (_i64, [_p]),
     "l2b_profile_step": (C.c_int, [_p, _i32, _i32, _p, _p]),
@@ -201,6 +202,15 @@ class Context:
         self._check(self.lib.dll.l2b_forward_batch(self._h, B, _ptr(tokens), _ptr(pos),
                                                    _ptr(logits), _ptr(am)))
         return logits, am
+
+    def prefill(self, tokens, pos0=0, seq=0, want_logits=True):
+        """All prompt positions in one pass (l2b_prefill).  Returns (last logits or None, argmax)."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        logits = np.empty(self.vocab_size, dtype=np.float32) if want_logits else None
+        am = _i32(0)
+        self._check(self.lib.dll.l2b_prefill(self._h, seq, tokens.size, _ptr(tokens), pos0, _ptr(logits),
+                                             C.byref(am)))
+        return logits, int(am.value)
 
     def generate_greedy(self, tokens, pos, n_steps, forced=None):
         """Device-resident greedy loop; returns int32[n_steps, B] of `next` tokens."""

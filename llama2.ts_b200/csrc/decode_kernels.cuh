@@ -605,6 +605,8 @@ struct AttnParams {
   float* xb;         // [B][xb_stride]  attention output
   const int* posp;   // [B]
   int H, hs, steps;
+  long long kv_b_stride;            // floats between the caches of consecutive batch entries (0: all
+                                    // entries read ONE sequence's cache -- prompt prefill)
   int q_stride, xb_stride, xb_off;  // xb_off: column offset of head 0 (tensor-parallel slice)
   int tileT;         // time steps per ring stage
   int sc_cap;        // floats reserved for scores per CTA
@@ -659,7 +661,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
   const int tileT = p.tileT;
   const int nTiles = (nT + tileT - 1) / tileT;
   const int total = 2 * nTiles;  // K tiles then V tiles
-  const size_t head_off = (((size_t)b * p.H + h) * p.steps) * hs;
+  const size_t head_off = (size_t)b * (size_t)p.kv_b_stride + ((size_t)h * p.steps) * hs;
   const float* kbase = p.kc + head_off + (size_t)t0 * hs;
   const float* vbase = p.vc + head_off + (size_t)t0 * hs;
   const int stage_floats = kAttnStageBytes / 4;

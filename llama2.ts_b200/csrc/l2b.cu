@@ -77,8 +77,13 @@ struct l2b_ctx {
   int* blk_idx = nullptr;
   int *d_forced = nullptr, *d_out = nullptr;
   unsigned* d_bar = nullptr;  // grid barrier words of the persistent kernel
+  // prompt prefill scratch (l2b_prefill): activations of `pf_cap` positions of one sequence
+  float *pf_x = nullptr, *pf_xb = nullptr, *pf_q = nullptr;
+  int *d_pfctl = nullptr, *h_pfctl = nullptr;
+  int pf_cap = 0;
   // batched tensor-core path: pre-split activations [256*groups][D or F], partial sums
   float *XhD = nullptr, *XlD = nullptr, *XhF = nullptr, *XlF = nullptr, *P = nullptr;
+  size_t P_floats = 0;
   int Bpad = 0, Smax = 8;
   std::map<std::pair<const void*, int>, CUtensorMap> tmaps;  // key: (operand base, box rows)
   // host staging (pinned)
@@ -370,19 +375,33 @@ int launch_gemm(l2b_ctx* c, int kclass, const float* W, int M, int K, const floa
   return 0;
 }
 
-int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
+// Which activations / cache rows a batched pass works on: B independent sequences (decode),
+// or B consecutive positions of ONE sequence (prompt prefill: every entry reads and writes
+// that sequence's cache, entry i at position pos0 + i).
+struct BatchView {
+  float *x, *xb, *q;
+  int* ctl;            // CTL header + tok[B] + pos[B]
+  size_t kv_off;       // floats from the layer base to the cache of entry 0
+  long long kv_stride; // floats between the caches of consecutive entries (0 for prefill)
+  int cls_mode;        // 0: classifier for every entry (batched decode); 1: last entry only;
+                       // 2: none (a prefill chunk that is not the last one)
+};
+
+int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v) {
   const int D = c->D, F = c->F, hs = c->hs, H = c->H, V = c->V;
   const size_t kv_seq = (size_t)H * c->steps * hs;
   const size_t kv_layer = kv_seq * c->Bmax;
-  const int* tokp = c->d_ctl + CTL_HDR;
-  const int* posp = c->d_ctl + CTL_HDR + B;
+  const int* tokp = v.ctl + CTL_HDR;
+  const int* posp = v.ctl + CTL_HDR + B;
   int rc, S = 1;
 
+  const BatchView* pv = &v;
   auto resid_rms = [&](const float* P, int Sp, const float* emb, const float* rms_w) -> int {
+    const BatchView& vw = *pv;
     BatVecParams v;
     memset(&v, 0, sizeof v);
     v.P = P; v.S = Sp; v.B = B; v.M = D;
-    v.tok_emb = emb; v.tokp = tokp; v.x = c->x; v.rms_w = rms_w;
+    v.tok_emb = emb; v.tokp = tokp; v.x = vw.x; v.rms_w = rms_w;
     v.xh = c->XhD; v.xl = c->XlD; v.D = D;
     void* args[] = {&v};
     return launch(c, L2B_K_BATCH_EPI, (const void*)bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
@@ -398,9 +417,9 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
       BatQkvParams q;
       memset(&q, 0, sizeof q);
       q.P = c->P; q.S = S; q.B = B; q.D = D; q.hs = hs; q.steps = c->steps;
-      q.posp = posp; q.fcr = c->fcr; q.fci = c->fci; q.q = c->q;
-      q.kc = c->kc + (size_t)l * kv_layer; q.vc = c->vc + (size_t)l * kv_layer;
-      q.kv_seq_stride = (long long)kv_seq;
+      q.posp = posp; q.fcr = c->fcr; q.fci = c->fci; q.q = v.q;
+      q.kc = c->kc + (size_t)l * kv_layer + v.kv_off; q.vc = c->vc + (size_t)l * kv_layer + v.kv_off;
+      q.kv_seq_stride = v.kv_stride;
       void* args[] = {&q};
       rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_qkv_epi_kernel, dim3((3 * D / 2 + 255) / 256, B), dim3(256), 0,
                   1, args, st);
@@ -409,12 +428,13 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
     {
       AttnParams a;
       memset(&a, 0, sizeof a);
-      a.q = c->q;
-      a.kc = c->kc + (size_t)l * kv_layer;
-      a.vc = c->vc + (size_t)l * kv_layer;
-      a.xb = c->xb;
+      a.q = v.q;
+      a.kc = c->kc + (size_t)l * kv_layer + v.kv_off;
+      a.vc = c->vc + (size_t)l * kv_layer + v.kv_off;
+      a.xb = v.xb;
       a.posp = posp;
       a.H = H; a.hs = hs; a.steps = c->steps;
+      a.kv_b_stride = v.kv_stride;
       a.q_stride = D; a.xb_stride = D; a.xb_off = 0;
       a.tileT = kAttnStageBytes / (hs * 4);
       a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
@@ -446,17 +466,35 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st) {
     rc = resid_rms(c->P, S, nullptr, l + 1 < c->L ? c->rms_att + (size_t)(l + 1) * D : c->rms_final);
     if (rc) return rc;
   }
+  if (v.cls_mode == 2) return 0;
+  if (v.cls_mode == 1) {
+    // prefill: only the last position's logits exist in the reference's state afterwards
+    // (llama2.ts:468-473 overwrites s.logits every step); classifier as a batch-1 matvec
+    GemvParams p;
+    memset(&p, 0, sizeof p);
+    p.W = c->wcls; p.rows = V; p.n = D;
+    p.vin = v.x + (size_t)(B - 1) * D; p.vin_stride = D;
+    p.rms_w = c->rms_final;
+    p.logits = c->logits; p.V = V;
+    p.tokp = v.ctl + CTL_HDR; p.posp = v.ctl + CTL_HDR + B;
+    p.x = v.x; p.xdim = D;
+    p.ctl = c->d_pfctl; p.ticket = c->d_dev; p.next = c->d_dev + 1;
+    p.forced = c->d_forced; p.out_tokens = c->d_out;
+    p.blk_val = c->blk_val; p.blk_idx = c->blk_idx;
+    p.evict_first = c->weight_bytes > (size_t)100 * 1024 * 1024;
+    return launch_gemv(c, L2B_K_CLS, p, 1, st);
+  }
   rc = launch_gemm(c, L2B_K_GEMM_CLS, c->wcls, V, D, c->XhD, c->XlD, B, &S, st);
   if (rc) return rc;
   {
     BatLogitsParams g;
     memset(&g, 0, sizeof g);
-    g.P = c->P; g.S = S; g.B = B; g.V = V; g.logits = c->logits; g.ctl = c->d_ctl;
+    g.P = c->P; g.S = S; g.B = B; g.V = V; g.logits = c->logits; g.ctl = v.ctl;
     g.next = c->d_dev + 1; g.forced = c->d_forced; g.out_tokens = c->d_out;
     void* args[] = {&g};
     rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_logits_kernel, dim3(B), dim3(1024), 0, 1, args, st);
     if (rc) return rc;
-    int* ctl = c->d_ctl;
+    int* ctl = v.ctl;
     void* args2[] = {&ctl};
     rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_step_kernel, dim3(1), dim3(32), 0, 1, args2, st);
     if (rc) return rc;
@@ -545,6 +583,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       a.H = Hl;
       a.hs = hs;
       a.steps = c->steps;
+      a.kv_b_stride = (long long)kv_seq;
       a.q_stride = Dl;
       a.xb_stride = D;
       a.xb_off = R * Dl;
@@ -638,8 +677,10 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
 // One decode step for B sequences: tokens/positions are read from d_ctl.
 int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   if (c->tp_size > 1) return enqueue_step_tp(c, st);
-  if (c->opt.tc_min_batch > 0 && B >= c->opt.tc_min_batch && c->P != nullptr)
-    return enqueue_step_batched(c, B, st);
+  if (c->opt.tc_min_batch > 0 && B >= c->opt.tc_min_batch && c->P != nullptr) {
+    BatchView v = {c->x, c->xb, c->q, c->d_ctl, 0, (long long)c->H * c->steps * c->hs, 0};
+    return enqueue_step_batched(c, B, st, v);
+  }
   const int D = c->D, F = c->F, hs = c->hs, H = c->H;
   const size_t kv_seq = (size_t)H * c->steps * hs;
   const size_t kv_layer = kv_seq * c->Bmax;
@@ -695,6 +736,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       a.H = H;
       a.hs = hs;
       a.steps = c->steps;
+      a.kv_b_stride = (long long)kv_seq;
       a.q_stride = D;
       a.xb_stride = D;
       a.xb_off = 0;
@@ -1048,6 +1090,7 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     TRY(dev_alloc(c, &c->XhF, (size_t)c->Bpad * sF + 64, true));
     TRY(dev_alloc(c, &c->XlF, (size_t)c->Bpad * sF + 64, true));
     TRY(dev_alloc(c, &c->P, (size_t)c->Smax * sB * Mmax, false));
+    c->P_floats = (size_t)c->Smax * sB * Mmax;
   }
   TRY(dev_alloc(c, &c->d_bar, 4, true));
   TRY(dev_alloc(c, &c->d_forced, (size_t)max_steps * sB, true));
@@ -1101,9 +1144,12 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
     c->x = c->xb = c->hb = c->logits = nullptr;
   }
   if (c->h_err) cudaFreeHost(c->h_err);
+  if (c->h_pfctl) cudaFreeHost(c->h_pfctl);
+  if (c->d_pfctl) cudaFree(c->d_pfctl);
   float* fl[] = {c->tok_emb, c->rms_att, c->wqkv, c->wo, c->rms_ffn, c->w13, c->w2, c->rms_final,
                  c->fcr, c->fci, c->shared_cls ? nullptr : c->wcls, c->x, c->xb, c->q, c->hb,
-                 c->logits, c->kc, c->vc, c->blk_val, c->XhD, c->XlD, c->XhF, c->XlF, c->P};
+                 c->logits, c->kc, c->vc, c->blk_val, c->XhD, c->XlD, c->XhF, c->XlF, c->P,
+                 c->pf_x, c->pf_xb, c->pf_q};
   for (float* p : fl)
     if (p) cudaFree(p);
   int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar};
@@ -1219,6 +1265,99 @@ L2B_API int l2b_forward(l2b_ctx* c, int32_t token, int32_t pos, float* logits_ou
 L2B_API int l2b_forward_argmax(l2b_ctx* c, int32_t token, int32_t pos, int32_t* next_out) {
   if (c && !next_out) return fail(c, L2B_EINVAL, "null next_out");
   return l2b_forward_batch(c, 1, &token, &pos, nullptr, next_out);
+}
+
+// Scratch for l2b_prefill: activations of up to `cap` prompt positions.
+static int ensure_prefill(l2b_ctx* c, int cap) {
+  const size_t D = c->D, F = c->F, V = c->V;
+  const size_t Mmax = (3 * D > 2 * F ? 3 * D : 2 * F) > V ? (3 * D > 2 * F ? 3 * D : 2 * F) : V;
+  int rc = 0;
+  if (cap > c->pf_cap) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->pf_x) { cudaFree(c->pf_x); cudaFree(c->pf_xb); cudaFree(c->pf_q); cudaFree(c->d_pfctl); cudaFreeHost(c->h_pfctl); }
+    c->pf_x = c->pf_xb = c->pf_q = nullptr; c->d_pfctl = nullptr; c->h_pfctl = nullptr; c->pf_cap = 0;
+    if (!rc) rc = dev_alloc(c, &c->pf_x, (size_t)cap * D, true);
+    if (!rc) rc = dev_alloc(c, &c->pf_xb, (size_t)cap * D, true);
+    if (!rc) rc = dev_alloc(c, &c->pf_q, (size_t)cap * D, true);
+    if (!rc) rc = dev_alloc(c, &c->d_pfctl, CTL_HDR + 2 * (size_t)cap, true);
+    if (!rc && cudaMallocHost((void**)&c->h_pfctl, sizeof(int) * (CTL_HDR + 2 * (size_t)cap)) != cudaSuccess)
+      rc = fail(c, L2B_ENOMEM, "pinned prefill header");
+    if (rc) return rc;
+    c->pf_cap = cap;
+  }
+  if (!c->XhD) {
+    c->Bpad = 256;
+    if (!rc) rc = dev_alloc(c, &c->XhD, (size_t)c->Bpad * D + 64, true);
+    if (!rc) rc = dev_alloc(c, &c->XlD, (size_t)c->Bpad * D + 64, true);
+    if (!rc) rc = dev_alloc(c, &c->XhF, (size_t)c->Bpad * F + 64, true);
+    if (!rc) rc = dev_alloc(c, &c->XlF, (size_t)c->Bpad * F + 64, true);
+    if (rc) return rc;
+  }
+  const size_t need = (size_t)c->Smax * cap * Mmax;
+  if (need > c->P_floats) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    drop_graphs(c);  // graphs captured the old pointer
+    if (c->P) cudaFree(c->P);
+    c->P = nullptr; c->P_floats = 0;
+    rc = dev_alloc(c, &c->P, need, false);
+    if (rc) return rc;
+    c->P_floats = need;
+  }
+  CU(c, cudaDeviceSynchronize());
+  return 0;
+}
+
+L2B_API int l2b_prefill(l2b_ctx* c, int32_t seq, int32_t n_tokens, const int32_t* tokens, int32_t pos0,
+                        float* logits_out, int32_t* argmax_out) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (c->tp_size > 1) return fail(c, L2B_ESTATE, "prefill is not available on a tensor-parallel context");
+  if (seq < 0 || seq >= c->Bmax) return fail(c, L2B_EINVAL, "seq %d outside [0,%d)", seq, c->Bmax);
+  if (n_tokens < 1 || !tokens) return fail(c, L2B_EINVAL, "n_tokens < 1 or null tokens");
+  if (pos0 < 0 || pos0 + n_tokens > c->steps)
+    return fail(c, L2B_EINVAL, "positions %d..%d outside the %d cached rows", pos0, pos0 + n_tokens - 1, c->steps);
+  if (pos0 > c->n_run[seq])
+    return fail(c, L2B_EORDER, "pos %d of sequence %d called before positions %d..%d were run", pos0, seq,
+                c->n_run[seq], pos0 - 1);
+  for (int i = 0; i < n_tokens; ++i)
+    if (tokens[i] < 0 || tokens[i] >= c->V) return fail(c, L2B_EINVAL, "token %d outside [0,%d)", tokens[i], c->V);
+  CU(c, cudaSetDevice(c->device));
+  const int cap = n_tokens < 256 ? (n_tokens < 32 ? 32 : n_tokens) : 256;
+  rc = ensure_prefill(c, cap);
+  if (rc) return rc;
+  const size_t kv_seq = (size_t)c->H * c->steps * c->hs;
+  const int64_t l0 = c->launch_counter;
+  CU(c, cudaEventRecord(c->ev0, c->stream));
+  for (int done = 0; done < n_tokens; done += c->pf_cap) {
+    const int B = (n_tokens - done) < c->pf_cap ? (n_tokens - done) : c->pf_cap;
+    const bool last = done + B == n_tokens;
+    if (done > 0) CU(c, cudaStreamSynchronize(c->stream));  // h_pfctl is reused
+    c->h_pfctl[CTL_STEP] = 0;
+    c->h_pfctl[CTL_USE_FORCED] = 0;
+    c->h_pfctl[CTL_ADVANCE] = 0;
+    c->h_pfctl[CTL_RESERVED] = 0;
+    for (int i = 0; i < B; ++i) {
+      c->h_pfctl[CTL_HDR + i] = tokens[done + i];
+      c->h_pfctl[CTL_HDR + B + i] = pos0 + done + i;
+    }
+    CU(c, cudaMemcpyAsync(c->d_pfctl, c->h_pfctl, sizeof(int) * (CTL_HDR + 2 * B), cudaMemcpyHostToDevice,
+                          c->stream));
+    BatchView v = {c->pf_x, c->pf_xb, c->pf_q, c->d_pfctl, (size_t)seq * kv_seq, 0, last ? 1 : 2};
+    rc = enqueue_step_batched(c, B, c->stream, v);
+    if (rc) return rc;
+  }
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  c->last_launches = c->launch_counter - l0;
+  if (logits_out)
+    CU(c, cudaMemcpyAsync(c->h_logits, c->logits, sizeof(float) * c->V, cudaMemcpyDeviceToHost, c->stream));
+  if (argmax_out)
+    CU(c, cudaMemcpyAsync(c->h_out, c->d_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  rc = finish(c);
+  if (rc) return rc;
+  if (logits_out) memcpy(logits_out, c->h_logits, sizeof(float) * c->V);
+  if (argmax_out) *argmax_out = c->h_out[0];
+  if (pos0 + n_tokens > c->n_run[seq]) c->n_run[seq] = pos0 + n_tokens;
+  return L2B_OK;
 }
 
 L2B_API int l2b_generate_greedy(l2b_ctx* c, int32_t B, const int32_t* tokens, const int32_t* pos,

@@ -198,7 +198,7 @@ def sample_topp(logits, topp, rng):
 # generate loop (llama2.ts:460-511)
 
 def generate(config, weights, state, steps, prompt_tokens, temperature, topp, rng, on_token=None,
-             device_greedy=False):
+             device_greedy=False, prefill=False):
     """The `while (pos < steps)` loop.  Returns (tokens, tok_per_s).
     device_greedy=True keeps the whole -t 0 loop on the device (l2b_generate_greedy):
     same tokens, no per-token round trip."""
@@ -216,11 +216,28 @@ def generate(config, weights, state, steps, prompt_tokens, temperature, topp, rn
             out.append(int(t))
             if t == 1:
                 break
+        prev = 1
         for t in out:
             if on_token and t != 1:
-                on_token(t)
+                on_token(t, prev)
+            prev = t
         return out, (len(out) / dt if dt > 0 else float("inf"))
     token, pos, start = 1, 0, 0.0
+    if prefill and n_prompt > 1 and n_prompt < steps:
+        # positions 0..n_prompt-1 only force the next prompt token (llama2.ts:471-473): run them
+        # as ONE batched pass (l2b_prefill) instead of n_prompt transformer() calls
+        fed = np.concatenate([[1], np.asarray(prompt_tokens[:n_prompt - 1], dtype=np.int32)])
+        weights.ctx.prefill(fed, 0, want_logits=False)
+        for i in range(n_prompt):
+            nxt = int(prompt_tokens[i])
+            out.append(nxt)
+            if nxt == 1:
+                return out, float("inf")
+            if on_token:
+                on_token(nxt, token)
+            token = nxt
+        pos = n_prompt
+        start = time.time()
     while pos < steps:
         transformer(token, pos, config, state, weights)          # llama2.ts:468
         if pos < n_prompt:
