@@ -524,6 +524,29 @@ def main():
             except Exception as e:  # never lose the headline line to a side measurement
                 others[name] = {"error": str(e)}
         line["others"] = others
+        try:   # checkpoint loader fast path vs the reference-order per-tensor reads
+            import tempfile
+            h3 = pkg.synth.header("stories110M")
+            with tempfile.TemporaryDirectory() as td:
+                fpath = pkg.synth.write_checkpoint(os.path.join(td, "m.bin"), h3, seed=1)
+                nbytes = os.path.getsize(fpath)
+                c3 = pkg.Context(h3, device=local_rank, max_steps=8)
+                c3.load_checkpoint(fpath)                      # page cache + allocator warm-up
+                fast = min(c3.load_checkpoint(fpath) for _ in range(3))
+                c3.close()
+                t0 = time.perf_counter()
+                with open(fpath, "rb") as f:
+                    cfg3 = pkg.host.readConfig(f.read(28))
+                    w3 = pkg.host.readWeights(cfg3, f, cfg3.shared_weights, device=local_rank, max_steps=8)
+                slow = time.perf_counter() - t0
+                w3.ctx.close()
+            line["loader"] = {"file_mb": nbytes / 1e6, "l2b_load_checkpoint_s": fast,
+                              "l2b_load_checkpoint_gbs": nbytes / fast / 1e9,
+                              "per_tensor_read_upload_s": slow, "per_tensor_gbs": nbytes / slow / 1e9,
+                              "note": "stories110M file from the page cache; per-tensor = readWeights() order "
+                                      "(llama2.ts:112-129) with one l2b_upload per slice"}
+        except Exception as e:
+            line["loader"] = {"error": str(e)}
 
     if rank == 0:
         print(json.dumps(line))

@@ -88,6 +88,13 @@ int l2b_create_tp(const int32_t hdr[7], int32_t device, int32_t max_steps,
 int l2b_upload(l2b_ctx* ctx, int32_t tensor_id, int32_t layer, const float* host,
                uint64_t n_floats);
 
+/* Checkpoint loader fast path: reads a llama2.c legacy-v0
+ * .bin (the file llama2.ts:427-436 opens) straight into the device layout through pinned
+ * double-buffered staging; equivalent to the l2b_upload calls of readWeights()
+ * (llama2.ts:112-129) in file order.  The header must match the context.  A tensor-parallel
+ * rank reads only its own rows.  seconds_out (may be NULL) receives the wall time.       */
+int l2b_load_checkpoint(l2b_ctx* ctx, const char* path, double* seconds_out);
+
 /* 1 when every tensor the config needs has been uploaded, else 0. */
 int l2b_weights_ready(const l2b_ctx* ctx);
 

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "l2b_create": (C.c_int, [C.POINTER(_i32), _i32, _i32, _i32, C.POINTER(_p)]),
     "l2b_create_tp": (C.c_int, [C.POINTER(_i32), _i32, _i32, _i32, _i32, C.POINTER(_p)]),
     "l2b_upload": (C.c_int, [_p, _i32, _i32, _p, _u64]),
+    "l2b_load_checkpoint": (C.c_int, [_p, C.c_char_p, C.POINTER(C.c_double)]),
     "l2b_weights_ready": (C.c_int, [_p]),
     "l2b_forward": (C.c_int, [_p, _i32, _i32, _p]),
     "l2b_forward_argmax": (C.c_int, [_p, _i32, _i32, C.POINTER(_i32)]),
@@ -176,6 +177,12 @@ class Context:
         else:
             n = n_floats
         self._check(self.lib.dll.l2b_upload(self._h, tensor_id, layer, _ptr(arr), n))
+
+    def load_checkpoint(self, path):
+        """Stream a legacy-v0 .bin file into HBM (l2b_load_checkpoint).  Returns seconds."""
+        secs = C.c_double(0.0)
+        self._check(self.lib.dll.l2b_load_checkpoint(self._h, os.fsencode(path), C.byref(secs)))
+        return float(secs.value)
 
     def weights_ready(self):
         return bool(self.lib.dll.l2b_weights_ready(self._h))

@@ -6,10 +6,14 @@
 // There is NO CPU implementation in this library: without a CUDA device
 // l2b_create fails with L2B_ECUDA.
 #include <cuda_runtime.h>
+#include <fcntl.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
+
+#include <chrono>
 
 #include <map>
 #include <utility>
@@ -1164,63 +1168,166 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
   delete c;
 }
 
-L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float* host,
-                       uint64_t n_floats) {
-  if (!c) return L2B_EINVAL;
-  if (!host) return fail(c, L2B_EINVAL, "null host pointer");
+// Where a tensor of the checkpoint lives on this context.  Row-sharded tensors keep rows
+// [rank*slice, (rank+1)*slice) of the FULL tensor (slice == all rows when tp_size == 1):
+// `src_off` floats of the full tensor are skipped, then `rows` rows of `row` floats follow.
+struct Placement {
+  float* dst;
+  size_t expect;     // floats of the full tensor (what the caller / the file holds)
+  size_t src_off;    // first float kept
+  size_t rows, row;  // kept rows x floats per row
+  size_t dst_pitch;  // floats between kept rows on the device (2*row for the w1/w3 interleave)
+};
+
+static int placement(l2b_ctx* c, int tensor_id, int layer, Placement* pl) {
   if (tensor_id < 0 || tensor_id >= L2B_T_COUNT) return fail(c, L2B_EINVAL, "tensor id %d", tensor_id);
   const size_t D = c->D, F = c->F, V = c->V, S = c->S, hs2 = c->hs / 2;
   const bool layered = (tensor_id >= L2B_T_RMS_ATT_WEIGHT && tensor_id <= L2B_T_W3);
   if (layer < 0 || layer >= (layered ? c->L : 1))
     return fail(c, L2B_EINVAL, "layer %d out of range for tensor %d", layer, tensor_id);
-  CU(c, cudaSetDevice(c->device));
-  // Row-sharded tensors keep rows [rank*slice, (rank+1)*slice) of the FULL tensor the caller
-  // passes (slice == all rows when tp_size == 1): `src_off` floats are skipped, `copy` copied.
   const size_t Dl = c->Dl, Fl = c->Fl, Vl = c->Vl, r = c->tp_rank;
-  size_t expect = 0, src_off = 0, copy = 0, w13_rows = 0;
-  float* dst = nullptr;
+  Placement p = {nullptr, 0, 0, 1, 0, 0};
   switch (tensor_id) {
-    case L2B_T_TOKEN_EMBEDDING_TABLE: expect = copy = V * D; dst = c->tok_emb; break;
-    case L2B_T_RMS_ATT_WEIGHT: expect = copy = D; dst = c->rms_att + layer * D; break;
+    case L2B_T_TOKEN_EMBEDDING_TABLE: p.expect = V * D; p.rows = V; p.row = D; p.dst = c->tok_emb; break;
+    case L2B_T_RMS_ATT_WEIGHT: p.expect = D; p.row = D; p.dst = c->rms_att + layer * D; break;
     case L2B_T_WQ:
     case L2B_T_WK:
     case L2B_T_WV:
-      expect = D * D; src_off = r * Dl * D; copy = Dl * D;
-      dst = c->wqkv + (size_t)layer * 3 * Dl * D + (size_t)(tensor_id - L2B_T_WQ) * Dl * D;
+      p.expect = D * D; p.src_off = r * Dl * D; p.rows = Dl; p.row = D;
+      p.dst = c->wqkv + (size_t)layer * 3 * Dl * D + (size_t)(tensor_id - L2B_T_WQ) * Dl * D;
       break;
-    case L2B_T_WO: expect = D * D; src_off = r * Dl * D; copy = Dl * D; dst = c->wo + (size_t)layer * Dl * D; break;
-    case L2B_T_RMS_FFN_WEIGHT: expect = copy = D; dst = c->rms_ffn + layer * D; break;
+    case L2B_T_WO:
+      p.expect = D * D; p.src_off = r * Dl * D; p.rows = Dl; p.row = D; p.dst = c->wo + (size_t)layer * Dl * D;
+      break;
+    case L2B_T_RMS_FFN_WEIGHT: p.expect = D; p.row = D; p.dst = c->rms_ffn + layer * D; break;
     case L2B_T_W1:
-    case L2B_T_W3:
-      expect = F * D; src_off = r * Fl * D; w13_rows = Fl;
-      dst = c->w13 + (size_t)layer * 2 * Fl * D + (tensor_id == L2B_T_W3 ? D : 0);
+    case L2B_T_W3:  // interleave rows: device row 2i = w1 row i, 2i+1 = w3 row i (pairs feed SwiGLU)
+      p.expect = F * D; p.src_off = r * Fl * D; p.rows = Fl; p.row = D; p.dst_pitch = 2 * D;
+      p.dst = c->w13 + (size_t)layer * 2 * Fl * D + (tensor_id == L2B_T_W3 ? D : 0);
       break;
-    case L2B_T_W2: expect = D * F; src_off = r * Dl * F; copy = Dl * F; dst = c->w2 + (size_t)layer * Dl * F; break;
-    case L2B_T_RMS_FINAL_WEIGHT: expect = copy = D; dst = c->rms_final; break;
-    case L2B_T_FREQ_CIS_REAL: expect = copy = S * hs2; dst = c->fcr; break;
-    case L2B_T_FREQ_CIS_IMAG: expect = copy = S * hs2; dst = c->fci; break;
+    case L2B_T_W2:
+      p.expect = D * F; p.src_off = r * Dl * F; p.rows = Dl; p.row = F; p.dst = c->w2 + (size_t)layer * Dl * F;
+      break;
+    case L2B_T_RMS_FINAL_WEIGHT: p.expect = D; p.row = D; p.dst = c->rms_final; break;
+    case L2B_T_FREQ_CIS_REAL: p.expect = S * hs2; p.rows = S; p.row = hs2; p.dst = c->fcr; break;
+    case L2B_T_FREQ_CIS_IMAG: p.expect = S * hs2; p.rows = S; p.row = hs2; p.dst = c->fci; break;
     case L2B_T_WCLS:
       if (c->shared_cls)
         return fail(c, L2B_ESTATE, "shared classifier: wcls aliases the embedding table (llama2.ts:127)");
-      expect = V * D; src_off = r * Vl * D; copy = Vl * D; dst = c->wcls; break;
+      p.expect = V * D; p.src_off = r * Vl * D; p.rows = Vl; p.row = D; p.dst = c->wcls;
+      break;
   }
-  if (n_floats != expect)
-    return fail(c, L2B_EINVAL, "tensor %d expects %zu floats, got %llu", tensor_id, expect,
+  if (p.dst_pitch == 0) p.dst_pitch = p.row;
+  *pl = p;
+  return 0;
+}
+
+L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float* host,
+                       uint64_t n_floats) {
+  if (!c) return L2B_EINVAL;
+  if (!host) return fail(c, L2B_EINVAL, "null host pointer");
+  Placement pl;
+  int rc = placement(c, tensor_id, layer, &pl);
+  if (rc) return rc;
+  if (n_floats != pl.expect)
+    return fail(c, L2B_EINVAL, "tensor %d expects %zu floats, got %llu", tensor_id, pl.expect,
                 (unsigned long long)n_floats);
+  CU(c, cudaSetDevice(c->device));
   // make sure no step is still reading the old contents
   CU(c, cudaStreamSynchronize(c->stream));
-  if (tensor_id == L2B_T_W1 || tensor_id == L2B_T_W3) {
-    // interleave rows: device row 2i = w1 row i, 2i+1 = w3 row i (pairs feed SwiGLU)
-    CU(c, cudaMemcpy2DAsync(dst, 2 * D * sizeof(float), host + src_off, D * sizeof(float), D * sizeof(float),
-                            w13_rows, cudaMemcpyDefault, c->stream));
-  } else {
-    CU(c, cudaMemcpyAsync(dst, host + src_off, copy * sizeof(float), cudaMemcpyDefault, c->stream));
-  }
+  CU(c, cudaMemcpy2DAsync(pl.dst, pl.dst_pitch * sizeof(float), host + pl.src_off, pl.row * sizeof(float),
+                          pl.row * sizeof(float), pl.rows, cudaMemcpyDefault, c->stream));
   // the copy runs on the ctx stream (device sources are asynchronous otherwise): the
   // caller may free `host` on return and the next step sees the new contents
   CU(c, cudaStreamSynchronize(c->stream));
   c->uploaded[(size_t)tensor_id * c->L + layer] = 1;
   return L2B_OK;
+}
+
+// Checkpoint loader fast path.  The reference reads the
+// llama2.c legacy-v0 file tensor by tensor into fresh Buffers (fs.readSync, llama2.ts:44-68,
+// 112-129); here the file streams through two pinned staging buffers, the H2D copy of one
+// overlapping the pread of the other, straight into the device layout (w1/w3 interleave,
+// q/k/v stacking).  Shard-aware: a tensor-parallel rank preads only its own rows.
+L2B_API int l2b_load_checkpoint(l2b_ctx* c, const char* path, double* seconds_out) {
+  if (!c || !path) return L2B_EINVAL;
+  CU(c, cudaSetDevice(c->device));
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(c, L2B_EINVAL, "cannot open %s", path);
+  int32_t hdr[7];
+  if (pread(fd, hdr, sizeof hdr, 0) != (ssize_t)sizeof hdr) {
+    close(fd);
+    return fail(c, L2B_EINVAL, "%s: short header", path);
+  }
+  const int V = hdr[5] < 0 ? -hdr[5] : hdr[5];
+  if (hdr[0] != c->D || hdr[1] != c->F || hdr[2] != c->L || hdr[3] != c->H || V != c->V || hdr[6] != c->S ||
+      (hdr[5] > 0) != c->shared_cls) {
+    close(fd);
+    return fail(c, L2B_EINVAL, "%s: header does not match the context's configuration", path);
+  }
+  const size_t kChunk = (size_t)32 << 20;
+  unsigned char* stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2];
+  cudaError_t e = cudaMallocHost((void**)&stage[0], kChunk);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&stage[1], kChunk);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    close(fd);
+    return fail(c, L2B_ENOMEM, "pinned staging: %s", cudaGetErrorString(e));
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  const auto t0 = std::chrono::steady_clock::now();
+  // file order (llama2.ts:114-127)
+  static const int order[] = {L2B_T_TOKEN_EMBEDDING_TABLE, L2B_T_RMS_ATT_WEIGHT, L2B_T_WQ, L2B_T_WK, L2B_T_WV,
+                              L2B_T_WO, L2B_T_RMS_FFN_WEIGHT, L2B_T_W1, L2B_T_W2, L2B_T_W3,
+                              L2B_T_RMS_FINAL_WEIGHT, L2B_T_FREQ_CIS_REAL, L2B_T_FREQ_CIS_IMAG, L2B_T_WCLS};
+  size_t file_off = sizeof hdr;
+  int rc = 0, slot = 0;
+  bool used[2] = {false, false};
+  for (int t : order) {
+    if (t == L2B_T_WCLS && c->shared_cls) continue;
+    const bool layered = (t >= L2B_T_RMS_ATT_WEIGHT && t <= L2B_T_W3);
+    for (int l = 0; l < (layered ? c->L : 1) && !rc; ++l) {
+      Placement pl;
+      rc = placement(c, t, l, &pl);
+      if (rc) break;
+      const size_t row_bytes = pl.row * sizeof(float);
+      size_t rows_per_chunk = kChunk / row_bytes;
+      if (rows_per_chunk == 0) { rc = fail(c, L2B_EINVAL, "row larger than the staging buffer"); break; }
+      for (size_t r0 = 0; r0 < pl.rows && !rc; r0 += rows_per_chunk) {
+        const size_t nr = (pl.rows - r0) < rows_per_chunk ? (pl.rows - r0) : rows_per_chunk;
+        if (used[slot]) cudaEventSynchronize(ev[slot]);  // the previous copy out of this buffer is done
+        const size_t want = nr * row_bytes;
+        size_t got = 0;
+        const off_t at = (off_t)(file_off + (pl.src_off + r0 * pl.row) * sizeof(float));
+        while (got < want) {
+          const ssize_t k = pread(fd, stage[slot] + got, want - got, at + (off_t)got);
+          if (k <= 0) { rc = fail(c, L2B_EINVAL, "%s: truncated at tensor %d layer %d", path, t, l); break; }
+          got += (size_t)k;
+        }
+        if (rc) break;
+        cudaError_t ce = cudaMemcpy2DAsync(pl.dst + r0 * pl.dst_pitch, pl.dst_pitch * sizeof(float), stage[slot],
+                                           row_bytes, row_bytes, nr, cudaMemcpyHostToDevice, c->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[slot], c->stream);
+        if (ce != cudaSuccess) { rc = fail(c, L2B_ECUDA, "H2D copy: %s", cudaGetErrorString(ce)); break; }
+        used[slot] = true;
+        slot ^= 1;
+      }
+      if (!rc) c->uploaded[(size_t)t * c->L + l] = 1;
+      file_off += pl.expect * sizeof(float);
+    }
+    if (rc) break;
+  }
+  cudaStreamSynchronize(c->stream);
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (seconds_out) *seconds_out = secs;
+  cudaFreeHost(stage[0]);
+  cudaFreeHost(stage[1]);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  close(fd);
+  return rc;
 }
 
 L2B_API int l2b_weights_ready(const l2b_ctx* c) {

@@ -27,7 +27,13 @@ hdr = pkg.synth.header(arch)
 _, blob = pkg.synth.checkpoint_blob(hdr, seed=41, std=0.04)
 V = abs(hdr[5])
 ctx = pkg.Context(hdr, device=rank, max_steps=steps, tp_rank=rank, tp_size=world)
-pkg.synth.upload_blob(ctx, hdr, blob)          # full tensors; the library keeps this rank's rows
+if arch == "wide":                             # shard-aware file loader: preads only this rank's rows
+    path = "/tmp/l2b_tp_%%d_%%d.bin" %% (os.getpid(), rank)
+    pkg.synth.write_checkpoint(path, hdr, seed=41, std=0.04)
+    ctx.load_checkpoint(path)
+    os.remove(path)
+else:
+    pkg.synth.upload_blob(ctx, hdr, blob)      # full tensors; the library keeps this rank's rows
 pkg.dist.connect_tp(ctx)
 toks = np.concatenate([[1], pkg.synth.teacher_tokens(steps - 1, V, 41)])
 single = pkg.Context(hdr, device=rank, max_steps=steps)
