@@ -49,6 +49,7 @@
 namespace l2b {
 
 constexpr int kGemmThreads = 384;
+constexpr int kGemmThreadsTmemA = 512;  // + a second splitter group (warps 12-15)
 constexpr int kBM = 128;                    // weight rows per tile (UMMA M)
 constexpr int kBK = 32;                     // floats per k-block: one 128-byte swizzle row
 constexpr int kTileA = kBM * kBK * 4;       // 16 KB
@@ -65,6 +66,9 @@ struct GemmParams {
   int n0;         // first column of this launch (batches > 256 run in column groups)
   int tiles_m;    // ceil(M / 128)
   int kblocks;    // ceil(K / 32)
+  const float* Xh; // pre-split activations, k-block-major + pre-swizzled: [K/32][npad][32 floats]
+  const float* Xl;
+  int npad;       // rows (sequences, padded) per k-block in Xh / Xl
   int dl;         // landing-ring depth (raw weight tiles in flight)
   int dop;        // operand-ring depth
   int rewrite_hi; // 1: weights' hi part rounded to nearest and rewritten in shared memory;
@@ -116,6 +120,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
 // Ring helper: slot index + phase parity of a circular buffer of `depth` slots.
 struct Ring {
   int i, ph, depth;
@@ -136,8 +152,7 @@ struct Ring {
 // operand slot; the long HBM latency is covered by the landing ring.
 template <int N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXh,
-                   const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ GemmParams p) {
+gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ GemmParams p) {
   constexpr int kTileX = N * kBK * 4;
   // N <= 128: the activation tiles travel with the weight tile in the landing ring (deep
   // prefetch of everything; HBM/L2-latency regime).  N = 256 is tensor-bound and its 64 KB of
@@ -185,8 +200,6 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
     mbar_fence_init();
     tmap_prefetch(&tmW);
-    tmap_prefetch(&tmXh);
-    tmap_prefetch(&tmXl);
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -245,8 +258,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         griddep_wait();  // X was written by the previous kernel
         for (int j = 0; j < ahead; ++j) {
           unsigned char* slot = land + (size_t)rx.i * kLandSlot;
-          tma_load_2d(slot + kTileA, &tmXh, x.kb * kBK, p.n0, &land_full[rx.i]);
-          tma_load_2d(slot + kTileA + kTileX, &tmXl, x.kb * kBK, p.n0, &land_full[rx.i]);
+          bulk_g2s(slot + kTileA, p.Xh + ((size_t)(x.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[rx.i]);
+          bulk_g2s(slot + kTileA + kTileX, p.Xl + ((size_t)(x.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[rx.i]);
           rx.next();
           x.next();
         }
@@ -257,8 +270,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
         tma_load_2d(slot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
         if (kXInLanding) {
-          tma_load_2d(slot + kTileA, &tmXh, a.kb * kBK, p.n0, &land_full[ra.i]);
-          tma_load_2d(slot + kTileA + kTileX, &tmXl, a.kb * kBK, p.n0, &land_full[ra.i]);
+          bulk_g2s(slot + kTileA, p.Xh + ((size_t)(a.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[ra.i]);
+          bulk_g2s(slot + kTileA + kTileX, p.Xl + ((size_t)(a.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[ra.i]);
         }
         ra.next();
         a.next();
@@ -277,8 +290,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           mbar_wait(&op_empty[ro.i], ro.ph ^ 1);
           unsigned char* slot = ops + (size_t)ro.i * kOpSlot;
           mbar_arrive_expect_tx(&op_xfull[ro.i], 2 * kTileX);
-          tma_load_2d(slot + kTileA, &tmXh, kb * kBK, p.n0, &op_xfull[ro.i]);
-          tma_load_2d(slot + kTileA + kTileX, &tmXl, kb * kBK, p.n0, &op_xfull[ro.i]);
+          bulk_g2s(slot + kTileA, p.Xh + ((size_t)(kb) * p.npad + p.n0) * kBK, kTileX, &op_xfull[ro.i]);
+          bulk_g2s(slot + kTileA + kTileX, p.Xl + ((size_t)(kb) * p.npad + p.n0) * kBK, kTileX, &op_xfull[ro.i]);
           ro.next();
         }
       }
@@ -429,8 +442,276 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------
+// Variant for N <= 128 with the WEIGHT operand in tensor memory.
+//
+// ncu on the kernel above at N = 32 (7B, 32 sequences): DRAM 43 %, tensor pipe 17 % -- it is
+// bound by shared-memory bandwidth: per 16 KB weight tile the MMAs re-read 32 KB of weight
+// operand (w_hi, w_lo) + 12 KB of activations from shared memory, on top of the TMA write
+// and the splitter's read + write.  Here the splitter (one thread per weight row) reads the
+// landed tile once and writes w_hi / w_lo with tcgen05.st into a 4-slot ring in TMEM (64
+// columns per slot); tcgen05.mma takes A from TMEM, so shared memory only sees the TMA write,
+// one read of the tile, and the small activation operand.
+// TMEM columns: [0,256) accumulators (2 sets x G pairs of (main | small)), [256,512) A ring.
+template <int N>
+__global__ void __launch_bounds__(kGemmThreadsTmemA, 1)
+gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ GemmParams p) {
+  static_assert(N == 32 || N == 64 || N == 128, "tensor-memory A variant: N <= 128");
+  constexpr int kTileX = N * kBK * 4;
+  constexpr int kLandSlot = kTileA + 2 * kTileX;   // raw weight tile | X_hi | X_lo
+  constexpr int kMaxDepth = 12;
+  constexpr int kASlots = 4, kASlotCols = 64, kAFirstCol = 256;
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+  constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | (8u << 24);
+  constexpr int G = N == 32 ? 2 : 1;               // (main | small) accumulator pairs per set
+  constexpr int kSetCols = G * 2 * N;              // 128 (N = 32, 64) or 256 (N = 128)
+  constexpr int kSets = N == 128 ? 1 : 2;
+  constexpr uint32_t kTmemCols = 512u;
+
+  extern __shared__ __align__(1024) unsigned char gsm[];
+  __shared__ __align__(8) uint64_t land_full[kMaxDepth], land_empty[kMaxDepth];
+  __shared__ __align__(8) uint64_t a_empty[kASlots], a_full[kASlots];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int DL = p.dl;
+  unsigned char* land = gsm + ((1024u - (smem_u32(gsm) & 1023u)) & 1023u);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DL; ++s) {
+      mbar_init(&land_full[s], 1);
+      mbar_init(&land_empty[s], 1);
+    }
+    for (int s = 0; s < kASlots; ++s) {
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&a_full[s], 4);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    mbar_fence_init();
+    tmap_prefetch(&tmW);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int n_items = p.tiles_m * p.S;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (same as above) ----------------
+    if (lane == 0) {
+      struct Seq {
+        int it, kb, kb1, mt;
+        const GemmParams& p;
+        int n_items, stride;
+        __device__ Seq(const GemmParams& p_, int first, int n, int st) : p(p_), n_items(n), stride(st) {
+          it = first;
+          load();
+        }
+        __device__ void load() {
+          if (it < n_items) {
+            const int split = it / p.tiles_m;
+            mt = it - split * p.tiles_m;
+            kb = (int)(((long long)p.kblocks * split) / p.S);
+            kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
+          }
+        }
+        __device__ bool done() const { return it >= n_items; }
+        __device__ void next() {
+          if (++kb >= kb1) {
+            it += stride;
+            load();
+          }
+        }
+      };
+      Seq a(p, blockIdx.x, n_items, gridDim.x), x(p, blockIdx.x, n_items, gridDim.x);
+      Ring ra(DL), rx(DL);
+      int ahead = 0;
+      while (!a.done() && ahead < DL) {
+        mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
+        tma_load_2d(land + (size_t)ra.i * kLandSlot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
+        ra.next();
+        a.next();
+        ++ahead;
+      }
+      griddep_wait();
+      for (int j = 0; j < ahead; ++j) {
+        unsigned char* slot = land + (size_t)rx.i * kLandSlot;
+        bulk_g2s(slot + kTileA, p.Xh + ((size_t)(x.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[rx.i]);
+        bulk_g2s(slot + kTileA + kTileX, p.Xl + ((size_t)(x.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[rx.i]);
+        rx.next();
+        x.next();
+      }
+      while (!a.done()) {
+        mbar_wait(&land_empty[ra.i], ra.ph ^ 1);
+        unsigned char* slot = land + (size_t)ra.i * kLandSlot;
+        mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
+        tma_load_2d(slot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
+        bulk_g2s(slot + kTileA, p.Xh + ((size_t)(a.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[ra.i]);
+        bulk_g2s(slot + kTileA + kTileX, p.Xl + ((size_t)(a.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[ra.i]);
+        ra.next();
+        a.next();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: A from tensor memory ----------------
+    if (lane == 0) {
+      Ring rl(DL), ro(kASlots);
+      int li = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+        const int split = it / p.tiles_m;
+        const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
+        const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
+        const int set = li % kSets;
+        mbar_wait(&tmem_empty_bar[set], ((li / kSets) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tset = tmem_base + (uint32_t)(set * kSetCols);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int kk = kb - kb0;
+          const uint32_t d_main = tset + (uint32_t)((kk % G) * 2 * N);
+          const uint32_t d_small = d_main + (uint32_t)N;
+          const uint32_t acc0 = kk >= G ? 1u : 0u;
+          mbar_wait(&a_full[ro.i], ro.ph);  // w_hi / w_lo of this k-block are in TMEM (=> tile landed)
+          tc_fence_after();
+          unsigned char* ls = land + (size_t)rl.i * kLandSlot;
+          const uint64_t dXh = umma_desc_sw128(ls + kTileA);
+          const uint32_t a_hi = tmem_base + (uint32_t)(kAFirstCol + ro.i * kASlotCols);
+          const uint32_t a_lo = a_hi + 32u;
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+            const uint32_t acc = k != 0 ? 1u : acc0;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_main),
+                "r"(a_hi + (uint32_t)(k * 8)), "l"(dXh + adv), "r"(kIdesc2), "r"(acc)
+                : "memory");  // w_hi * [x_hi ; x_lo]
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_small),
+                "r"(a_lo + (uint32_t)(k * 8)), "l"(dXh + adv), "r"(kIdesc), "r"(1u)
+                : "memory");  // w_lo * x_hi
+          }
+          tc_commit(&land_empty[rl.i]);
+          tc_commit(&a_empty[ro.i]);
+          rl.next();
+          ro.next();
+        }
+        tc_commit(&tmem_full_bar[set]);
+      }
+    }
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+    // ---------------- splitter: one thread per weight row, shared memory -> TMEM ----------------
+    // Two groups of four warps (4-7 and 12-15; warp % 4 selects the TMEM lane quadrant) take
+    // alternate k-blocks, so that one group's tcgen05.st latency hides behind the other's loads.
+    const int grp = warp >= 12 ? 1 : 0;
+    const int row = (warp & 3) * 32 + lane;   // 0..127 == TMEM lane
+    int total = 0;                            // k-blocks this CTA processes over all its items
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int split = it / p.tiles_m;
+      total += (int)(((long long)p.kblocks * (split + 1)) / p.S) - (int)(((long long)p.kblocks * split) / p.S);
+    }
+    for (int n = grp; n < total; n += 2) {
+      const int ls = n % DL, lph = (n / DL) & 1;
+      const int as = n % kASlots, aph = (n / kASlots) & 1;
+      mbar_wait(&a_empty[as], aph ^ 1);
+      tc_fence_after();
+      mbar_wait(&land_full[ls], lph);
+      const unsigned char* tile = land + (size_t)ls * kLandSlot + (size_t)row * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // logical 16-byte chunk j sits at (j ^ (row & 7)) (SWIZZLE_128B)
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + ((j ^ (row & 7)) << 4));
+        hi[4 * j + 0] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+        lo[4 * j + 0] = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & kHiMask));
+        lo[4 * j + 1] = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & kHiMask));
+        lo[4 * j + 2] = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & kHiMask));
+        lo[4 * j + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & kHiMask));
+      }
+      const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAFirstCol + as * kASlotCols);
+      tmem_st32(ta, hi);        // the tensor core ignores the low 13 bits: raw words are w_hi
+      tmem_st32(ta + 32u, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[as]);
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // ---------------- epilogue (same as above) ----------------
+    const int wq = warp & 3;
+    int li = 0;
+    griddep_wait();
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+      const int split = it / p.tiles_m, mt = it - split * p.tiles_m;
+      const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
+      const int kb1 = (int)(((long long)p.kblocks * (split + 1)) / p.S);
+      const int set = li % kSets;
+      mbar_wait(&tmem_full_bar[set], (li / kSets) & 1);
+      tc_fence_after();
+      const int m = mt * kBM + wq * 32 + lane;
+      float* out = p.P + ((size_t)split * p.B + p.n0) * p.M + m;
+      const int used = (kb1 - kb0) < G ? (kb1 - kb0) : G;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * kSetCols);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        if (p.n0 + c0 >= p.B) break;
+        uint32_t r[32];
+        float sum[32];
+        tmem_ld32(lane_base + (uint32_t)c0, r);                       // main accumulators first
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
+#pragma unroll 1
+        for (int g = 1; g < used; ++g) {
+          tmem_ld32(lane_base + (uint32_t)(g * 2 * N + c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+        }
+#pragma unroll 1
+        for (int g = 0; g < used; ++g) {                              // then the small terms
+          tmem_ld32(lane_base + (uint32_t)(g * 2 * N + N + c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
+        }
+        if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (p.n0 + c0 + j < p.B) out[(size_t)(c0 + j) * p.M] = sum[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[set]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
 // fused elementwise kernels between the GEMMs (CUDA cores; activations are tiny)
 // ---------------------------------------------------------------------------
+// Activation operand layout the GEMMs read with ONE contiguous bulk copy per k-block:
+// k-block-major [K/32][npad rows][32 floats], each row's eight 16-byte chunks already in
+// SWIZZLE_128B order (chunk c of row b at position c ^ (b & 7)) -- exactly the shared-memory
+// image tcgen05.mma expects, so no tensor map (and none of its per-row requests) is needed.
+__device__ __forceinline__ size_t xsw_index(int b, int j, int npad) {
+  return ((size_t)(j >> 5) * npad + b) * 32 + ((((j >> 2) & 7) ^ (b & 7)) << 2) + (j & 3);
+}
 __device__ __forceinline__ void store_split(float* xh, float* xl, size_t i, float v) {
   const float h = __uint_as_float(tf32_hi_bits(__float_as_uint(v)));
   xh[i] = h;
@@ -444,8 +725,9 @@ struct BatVecParams {
   const int* tokp;
   float* x;              // [B][D]
   const float* rms_w;    // rmsnorm weight of the NEXT projection
-  float* xh;             // [Bpad][D] pre-split normalised activations
+  float* xh;             // pre-split normalised activations (xsw_index layout)
   float* xl;
+  int npad;
   int D;
 };
 
@@ -480,7 +762,7 @@ __global__ void __launch_bounds__(256) bat_resid_rms_kernel(const __grid_constan
   tot = 1.0 / sqrt(1e-5 + tot);
   for (int j = threadIdx.x; j < D; j += 256) {
     const float o = (float)((double)__ldg(p.rms_w + j) * (tot * (double)x[j]));
-    store_split(p.xh, p.xl, (size_t)b * D + j, o);
+    store_split(p.xh, p.xl, xsw_index(b, j, p.npad), o);
   }
 }
 
@@ -532,8 +814,9 @@ __global__ void __launch_bounds__(256) bat_qkv_epi_kernel(const __grid_constant_
 struct BatSwigluParams {
   const float* P;  // [S][B][2F], rows interleaved (2i = w1 row i, 2i+1 = w3 row i)
   int S, B, F;
-  float* xh;       // [Bpad][F]
+  float* xh;       // xsw_index layout
   float* xl;
+  int npad;
 };
 
 // SwiGLU (llama2.ts:284-289) -> pre-split input of the w2 GEMM
@@ -551,7 +834,7 @@ __global__ void __launch_bounds__(256) bat_swiglu_kernel(const __grid_constant__
   }
   const double hv = (double)h1;
   const float silu = (float)(hv * (1.0 / (1.0 + exp(-hv))));
-  store_split(p.xh, p.xl, (size_t)b * p.F + i, (float)((double)silu * (double)h3));
+  store_split(p.xh, p.xl, xsw_index(b, i, p.npad), (float)((double)silu * (double)h3));
 }
 
 struct BatLogitsParams {

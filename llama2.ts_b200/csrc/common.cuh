@@ -123,6 +123,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
       ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// asynchronous bulk prefetch of a global range into L2 (no destination, no completion event)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* g, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
 // generic-proxy writes -> visible to the async proxy (TMA / tcgen05 reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

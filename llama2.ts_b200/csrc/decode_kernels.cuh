@@ -152,6 +152,7 @@ struct GemvParams {
   // batch slice handled by this launch
   int b0, nact, B;
   int evict_first;
+  int l2_prefetch;       // bytes of this CTA's weight range pulled into L2 before griddep_wait()
   TpParams tp;           // used by the TP = true instantiations only
 };
 
@@ -261,6 +262,21 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
   if (my_pairs > 0) {
     const float4* w0 = W4 + (size_t)(2 * pair) * n4;
     load_pair_tile(cur, w0, w0 + n4, lane, n4, pol);
+  }
+  // The HBM pipe idles between two kernels (tail of the previous one, launch, our prologue).
+  // Fill that time: pull the head of this CTA's weight range into L2 now, so that the main
+  // loop's next tiles are L2 hits while the stream behind them ramps up.
+  if (p.l2_prefetch > 0 && lane == 0) {
+    const size_t cta_bytes = (size_t)(pair1 - pair0) * 2 * n * sizeof(float);
+    size_t want = (size_t)p.l2_prefetch < cta_bytes ? (size_t)p.l2_prefetch : cta_bytes;
+    const size_t per = ((want / WARPS) + 15) & ~(size_t)15;
+    const size_t off = (size_t)warp * per;
+    if (per > 0 && off < want) {
+      const size_t len = (off + per <= want) ? per : ((want - off) & ~(size_t)15);
+      if (len > 0)
+        prefetch_l2_bulk(reinterpret_cast<const unsigned char*>(p.W) + (size_t)pair0 * 2 * n * sizeof(float) + off,
+                         (uint32_t)len);
+    }
   }
 
   // ---- everything below may depend on the previous kernel ----
@@ -619,6 +635,11 @@ struct AttnParams {
   // batched tensor-core path: also emit the TF32 hi/lo split of the output (input of the wo GEMM)
   float* xh;
   float* xl;
+  int x_npad;
+  // attention is latency-bound and leaves HBM idle: meanwhile pull the NEXT kernel's weights
+  // (wo of this layer) into L2
+  const unsigned char* pf_ptr;
+  long long pf_bytes;
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __grid_constant__ AttnParams p) {
@@ -679,6 +700,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
   };
   if (tid == 0)
     for (int j = 0; j < kAttnStages - 1 && j < total; ++j) issue(j);
+  if (p.pf_bytes > 0 && tid == 0) {
+    // behind our own K/V requests in the copy queue: one slice of the next kernel's weights
+    const long long n_cta = (long long)gridDim.x * gridDim.y * gridDim.z;
+    const long long me = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const long long per = ((p.pf_bytes / n_cta) + 15) & ~15LL;
+    long long off = me * per;
+    const long long end = off + per < p.pf_bytes ? off + per : p.pf_bytes;
+    for (; off + 16 <= end; off += 65536) {
+      const long long len = (end - off < 65536 ? end - off : 65536) & ~15LL;
+      if (len > 0) prefetch_l2_bulk(p.pf_ptr + off, (uint32_t)len);
+    }
+  }
 
   // lane layout: G lanes cover one cache row (hs floats) as float4s
   const int G = hs4 <= 16 ? 16 : 32;
@@ -819,8 +852,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
     const size_t o = (size_t)b * p.xb_stride + p.xb_off + (size_t)h * hs + tid;
     if (p.xh != nullptr) {
       const float hi = __uint_as_float((__float_as_uint(s) + 0x1000u) & 0xFFFFE000u);
-      p.xh[o] = hi;
-      p.xl[o] = s - hi;
+      const int j = (int)(h * hs + tid);  // column of this element; rows = batch entries
+      const size_t xi = ((size_t)(j >> 5) * p.x_npad + b) * 32 + ((((j >> 2) & 7) ^ (b & 7)) << 2) + (j & 3);
+      p.xh[xi] = hi;
+      p.xl[xi] = s - hi;
     }
     if (p.tp_size <= 1) {
       p.xb[o] = s;

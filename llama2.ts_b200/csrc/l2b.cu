@@ -45,6 +45,10 @@ struct Options {
   int tc_min_batch = 5;  // batches >= this run the tcgen05 GEMM path (0 = never)
   int tc_splits = 0;     // 0 = auto k-split per GEMM
   int tc_rewrite_hi = 0; // see GemmParams::rewrite_hi
+  int tc_tmem_a = 1;     // N <= 128: weight operand in tensor memory (gemm_3xtf32_tmemA_kernel)
+  int l2_prefetch = 262144;  // bytes per CTA prefetched into L2 before griddep_wait (0 = off)
+  int attn_prefetch = 0;     // attention kernel prefetches the wo weights into L2 (measured net-negative: it
+                             // delays the K/V copies in the same queue; kept as an option)
   int mega = 0;          // batch-1: whole step (and greedy loop) as one persistent cooperative kernel
                          // (experiment, opt-in: measured slower than graph+PDL so far)
 };
@@ -346,15 +350,12 @@ int launch_gemm(l2b_ctx* c, int kclass, const float* W, int M, int K, const floa
   for (int n0 = 0; n0 < B; n0 += 256) {
     const int cols = (B - n0) < 256 ? (B - n0) : 256;
     const int N = gemm_n_for(cols);
-    const CUtensorMap *tW, *tXh, *tXl;
+    const CUtensorMap* tW;
     int rc = get_tmap(c, W, M, K, kBM, &tW);
-    if (rc) return rc;
-    rc = get_tmap(c, Xh, c->Bpad, K, N, &tXh);
-    if (rc) return rc;
-    rc = get_tmap(c, Xl, c->Bpad, K, N, &tXl);
     if (rc) return rc;
     GemmParams g;
     g.P = c->P;
+    g.Xh = Xh; g.Xl = Xl; g.npad = c->Bpad;
     g.M = M; g.K = K; g.S = S; g.B = B; g.n0 = n0;
     g.tiles_m = (M + kBM - 1) / kBM;
     g.kblocks = (K + kBK - 1) / kBK;
@@ -369,11 +370,23 @@ int launch_gemm(l2b_ctx* c, int kclass, const float* W, int M, int K, const floa
                    : N == 64 ? (const void*)gemm_3xtf32_kernel<64>
                    : N == 128 ? (const void*)gemm_3xtf32_kernel<128>
                               : (const void*)gemm_3xtf32_kernel<256>;
+    size_t smem_bytes = (size_t)g.dl * land_slot + (size_t)g.dop * op_slot + 1024;
+    int threads = kGemmThreads;
+    if (c->opt.tc_tmem_a && N <= 128) {
+      // weight operand in tensor memory: no operand ring in shared memory, all of it is landing ring
+      fn = N == 32 ? (const void*)gemm_3xtf32_tmemA_kernel<32>
+         : N == 64 ? (const void*)gemm_3xtf32_tmemA_kernel<64>
+                   : (const void*)gemm_3xtf32_tmemA_kernel<128>;
+      g.dl = (224 * 1024) / land_slot;
+      if (g.dl > 12) g.dl = 12;
+      smem_bytes = (size_t)g.dl * land_slot + 1024;
+      threads = kGemmThreadsTmemA;
+    }
     int items = g.tiles_m * S;
     const int grid = items < c->num_sms ? items : c->num_sms;
-    CUtensorMap a = *tW, b = *tXh, d = *tXl;
-    void* args[] = {&a, &b, &d, &g};
-    rc = launch(c, kclass, fn, dim3(grid), dim3(kGemmThreads), (size_t)g.dl * land_slot + (size_t)g.dop * op_slot + 1024, 1, args, st);
+    CUtensorMap a = *tW;
+    void* args[] = {&a, &g};
+    rc = launch(c, kclass, fn, dim3(grid), dim3(threads), smem_bytes, 1, args, st);
     if (rc) return rc;
   }
   return 0;
@@ -406,7 +419,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
     memset(&v, 0, sizeof v);
     v.P = P; v.S = Sp; v.B = B; v.M = D;
     v.tok_emb = emb; v.tokp = tokp; v.x = vw.x; v.rms_w = rms_w;
-    v.xh = c->XhD; v.xl = c->XlD; v.D = D;
+    v.xh = c->XhD; v.xl = c->XlD; v.npad = c->Bpad; v.D = D;
     void* args[] = {&v};
     return launch(c, L2B_K_BATCH_EPI, (const void*)bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
   };
@@ -443,7 +456,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
       a.tileT = kAttnStageBytes / (hs * 4);
       a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
       a.tp_size = 1;
-      a.xh = c->XhD; a.xl = c->XlD;
+      a.xh = c->XhD; a.xl = c->XlD; a.x_npad = c->Bpad;
       const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
       rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B), dim3(kAttnThreads), smem, cs,
@@ -459,7 +472,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
     {
       BatSwigluParams w;
       memset(&w, 0, sizeof w);
-      w.P = c->P; w.S = S; w.B = B; w.F = F; w.xh = c->XhF; w.xl = c->XlF;
+      w.P = c->P; w.S = S; w.B = B; w.F = F; w.xh = c->XhF; w.xl = c->XlF; w.npad = c->Bpad;
       void* args[] = {&w};
       rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_swiglu_kernel, dim3((F + 255) / 256, B), dim3(256), 0, 1, args,
                   st);
@@ -710,6 +723,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   base.blk_val = c->blk_val;
   base.blk_idx = c->blk_idx;
   base.evict_first = ef;
+  base.l2_prefetch = ef ? c->opt.l2_prefetch : 0;  // L2-resident models need no prefetch
 
   const int cs = auto_cluster(c, B);
   for (int l = 0; l < c->L; ++l) {
@@ -747,6 +761,10 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       a.tileT = kAttnStageBytes / (hs * 4);
       a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
       a.tp_size = 1;
+      if (ef && c->opt.attn_prefetch) {
+        a.pf_ptr = reinterpret_cast<const unsigned char*>(c->wo + (size_t)l * D * D);
+        a.pf_bytes = (long long)D * D * sizeof(float);
+      }
       const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
       int rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B),
@@ -1089,10 +1107,10 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     // tensor-core path scratch: activations padded to whole 256-column groups
     c->Bpad = ((max_batch + 255) / 256) * 256;
     const size_t Mmax = (size_t)(3 * D > 2 * F ? 3 * D : 2 * F) > sV ? (size_t)(3 * D > 2 * F ? 3 * D : 2 * F) : sV;
-    TRY(dev_alloc(c, &c->XhD, (size_t)c->Bpad * sD + 64, true));
-    TRY(dev_alloc(c, &c->XlD, (size_t)c->Bpad * sD + 64, true));
-    TRY(dev_alloc(c, &c->XhF, (size_t)c->Bpad * sF + 64, true));
-    TRY(dev_alloc(c, &c->XlF, (size_t)c->Bpad * sF + 64, true));
+    TRY(dev_alloc(c, &c->XhD, (size_t)c->Bpad * ((sD + 31) & ~(size_t)31), true));
+    TRY(dev_alloc(c, &c->XlD, (size_t)c->Bpad * ((sD + 31) & ~(size_t)31), true));
+    TRY(dev_alloc(c, &c->XhF, (size_t)c->Bpad * ((sF + 31) & ~(size_t)31), true));
+    TRY(dev_alloc(c, &c->XlF, (size_t)c->Bpad * ((sF + 31) & ~(size_t)31), true));
     TRY(dev_alloc(c, &c->P, (size_t)c->Smax * sB * Mmax, false));
     c->P_floats = (size_t)c->Smax * sB * Mmax;
   }
@@ -1394,10 +1412,10 @@ static int ensure_prefill(l2b_ctx* c, int cap) {
   }
   if (!c->XhD) {
     c->Bpad = 256;
-    if (!rc) rc = dev_alloc(c, &c->XhD, (size_t)c->Bpad * D + 64, true);
-    if (!rc) rc = dev_alloc(c, &c->XlD, (size_t)c->Bpad * D + 64, true);
-    if (!rc) rc = dev_alloc(c, &c->XhF, (size_t)c->Bpad * F + 64, true);
-    if (!rc) rc = dev_alloc(c, &c->XlF, (size_t)c->Bpad * F + 64, true);
+    if (!rc) rc = dev_alloc(c, &c->XhD, (size_t)c->Bpad * ((D + 31) & ~(size_t)31), true);
+    if (!rc) rc = dev_alloc(c, &c->XlD, (size_t)c->Bpad * ((D + 31) & ~(size_t)31), true);
+    if (!rc) rc = dev_alloc(c, &c->XhF, (size_t)c->Bpad * ((F + 31) & ~(size_t)31), true);
+    if (!rc) rc = dev_alloc(c, &c->XlF, (size_t)c->Bpad * ((F + 31) & ~(size_t)31), true);
     if (rc) return rc;
   }
   const size_t need = (size_t)c->Smax * cap * Mmax;
@@ -1613,8 +1631,14 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.evict_first = v < 0 ? -1 : (v != 0);
   } else if (k == "tc_min_batch") {
     o.tc_min_batch = v < 0 ? 0 : v;
+  } else if (k == "l2_prefetch") {
+    o.l2_prefetch = v < 0 ? 0 : v;
+  } else if (k == "attn_prefetch") {
+    o.attn_prefetch = v != 0;
   } else if (k == "mega") {
     o.mega = v != 0;
+  } else if (k == "tc_tmem_a") {
+    o.tc_tmem_a = v != 0;
   } else if (k == "tc_rewrite_hi") {
     o.tc_rewrite_hi = v != 0;
   } else if (k == "tc_splits") {
