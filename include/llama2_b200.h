@@ -180,6 +180,11 @@ int l2b_profile_batch(l2b_ctx* ctx, int32_t B, const int32_t* tokens, const int3
 int l2b_read_state(l2b_ctx* ctx, int32_t which, int32_t seq, int32_t layer, int32_t pos,
                    float* out, uint64_t n_floats);
 
+/* Debug aid: after l2b_set_option("gemm_timeline", 1) the w1/w3 GEMM records clock64()
+ * stamps of CTA 0's warp roles per k-block (8 int64 per k-block: producer issue, splitter
+ * slot free / tile landed / stored, MMA operands ready / issued); copies up to n of them.  */
+int l2b_debug_timeline(l2b_ctx* ctx, int64_t* out, uint64_t n);
+
 /* Forget every sequence: zero the KV cache (newRunState, llama2.ts:160-161) and
  * allow pos to start again from 0.  Weights stay.                              */
 int l2b_reset(l2b_ctx* ctx);

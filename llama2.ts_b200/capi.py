@@ -64,6 +64,7 @@ _SIGNATURES = {
     "l2b_profile_batch": (C.c_int, [_p, _i32, _p, _p, _p, _p]),
     "l2b_read_state": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _u64]),
     "l2b_reset": (C.c_int, [_p]),
+    "l2b_debug_timeline": (C.c_int, [_p, _p, _u64]),
     "l2b_set_option": (C.c_int, [_p, C.c_char_p, _i64]),
     "l2b_tp_export": (_i64, [_p, _p, _u64]),
     "l2b_tp_connect": (C.c_int, [_p, C.c_char_p, _u64, _i32]),
@@ -274,6 +275,11 @@ class Context:
         assert all(len(b) == n for b in blobs)
         joined = b"".join(blobs)
         self._check(self.lib.dll.l2b_tp_connect(self._h, joined, n, len(blobs)))
+
+    def debug_timeline(self):
+        out = np.zeros((256, 8), dtype=np.int64)
+        self._check(self.lib.dll.l2b_debug_timeline(self._h, _ptr(out), out.size))
+        return out
 
     def reset(self):
         self._check(self.lib.dll.l2b_reset(self._h))

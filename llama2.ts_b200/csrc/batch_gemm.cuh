@@ -22,7 +22,10 @@
 // landing in adjacent accumulators (main | small); w_lo*x_hi is a second MMA of width N into
 // the small one.  At small N the MMA is bound by its shared-memory operand reads, and this
 // reads the 4 KB weight operand twice instead of three times per K=8 step.
-// Weights arrive ONCE from HBM as fp32 through TMA (SWIZZLE_128B tiles); four
+// Weights arrive ONCE from HBM as fp32 through TMA bulk copies.  They are kept in a second,
+// TILE-MAJOR copy ([tile][k-block][128 rows][32 floats], rows pre-swizzled to the
+// SWIZZLE_128B image tcgen05.mma expects) so that every 16 KB operand tile is ONE contiguous
+// cp.async.bulk (no tensor map, no per-row requests).  Four
 // "splitter" warps derive the hi/lo tiles in shared memory in place (an elementwise
 // rewrite, so the swizzled layout is preserved), the activations are pre-split by
 // the epilogue kernel that produced them.
@@ -66,11 +69,13 @@ struct GemmParams {
   int n0;         // first column of this launch (batches > 256 run in column groups)
   int tiles_m;    // ceil(M / 128)
   int kblocks;    // ceil(K / 32)
+  const float* Wt; // weights, tile-major + pre-swizzled: [tiles_m][kblocks][128 rows][32 floats]
   const float* Xh; // pre-split activations, k-block-major + pre-swizzled: [K/32][npad][32 floats]
   const float* Xl;
   int npad;       // rows (sequences, padded) per k-block in Xh / Xl
   int dl;         // landing-ring depth (raw weight tiles in flight)
   int dop;        // operand-ring depth
+  long long* dbg; // optional timeline of CTA 0 (clock64 per role per k-block), nullptr = off
   int rewrite_hi; // 1: weights' hi part rounded to nearest and rewritten in shared memory;
                   // 0: hi = hardware truncation of the raw tile (saves 16 KB of st.shared per k-block)
 };
@@ -84,6 +89,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 }
 __device__ __forceinline__ void tmap_prefetch(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+// One lane of a CONVERGED warp (cute::elect_one_sync).  Unlike `if (lane == 0)`, the
+// compiler knows the operands computed by the whole warp are uniform and feeds tcgen05 /
+// bulk-copy instructions from uniform registers directly; with `lane == 0` it wrapped every
+// tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA waterfall loop (~70 cycles per MMA,
+// measured with the kernel timeline: the MMA issuer was the bottleneck at small N).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -152,7 +167,7 @@ struct Ring {
 // operand slot; the long HBM latency is covered by the landing ring.
 template <int N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ GemmParams p) {
+gemm_3xtf32_kernel(const __grid_constant__ GemmParams p) {
   constexpr int kTileX = N * kBK * 4;
   // N <= 128: the activation tiles travel with the weight tile in the landing ring (deep
   // prefetch of everything; HBM/L2-latency regime).  N = 256 is tensor-bound and its 64 KB of
@@ -199,7 +214,6 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       mbar_init(&tmem_empty_bar[s], 4);
     }
     mbar_fence_init();
-    tmap_prefetch(&tmW);
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -249,7 +263,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       int ahead = 0;
       while (!a.done() && ahead < DL) {  // prologue: weights only
         mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
-        tma_load_2d(land + (size_t)ra.i * kLandSlot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
+        bulk_g2s(land + (size_t)ra.i * kLandSlot, p.Wt + ((size_t)(a.mt) * p.kblocks + (a.kb)) * (kBM * kBK), kTileA, &land_full[ra.i]);
         ra.next();
         a.next();
         ++ahead;
@@ -268,7 +282,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_wait(&land_empty[ra.i], ra.ph ^ 1);
         unsigned char* slot = land + (size_t)ra.i * kLandSlot;
         mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
-        tma_load_2d(slot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
+        bulk_g2s(slot, p.Wt + ((size_t)(a.mt) * p.kblocks + (a.kb)) * (kBM * kBK), kTileA, &land_full[ra.i]);
         if (kXInLanding) {
           bulk_g2s(slot + kTileA, p.Xh + ((size_t)(a.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[ra.i]);
           bulk_g2s(slot + kTileA + kTileX, p.Xl + ((size_t)(a.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[ra.i]);
@@ -297,8 +311,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (whole warp, one elected lane issues) ----------------
+    {
       Ring rl(DL), ro(DO);
       int li = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
@@ -327,7 +341,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           for (int k = 0; k < kBK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 step
             const uint32_t acc = k != 0 ? 1u : acc0;
-            if (kWide) {
+            if (!elect_one()) {
+            } else if (kWide) {
               tc_mma_tf32(d_main, dAh + adv, dXh + adv, kIdesc2, acc);   // w_hi * [x_hi ; x_lo]
               tc_mma_tf32(d_small, dAl + adv, dXh + adv, kIdesc, 1u);    // w_lo * x_hi
             } else {
@@ -335,13 +350,18 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
               tc_mma_tf32(d_small, dAh + adv, dXl + adv, kIdesc, 1u);
               tc_mma_tf32(d_main, dAh + adv, dXh + adv, kIdesc, acc);
             }
+            __syncwarp();
           }
-          tc_commit(&land_empty[rl.i]);  // both slots are free once these MMAs have read them
-          tc_commit(&op_empty[ro.i]);
+          if (elect_one()) {
+            tc_commit(&land_empty[rl.i]);  // both slots are free once these MMAs have read them
+            tc_commit(&op_empty[ro.i]);
+          }
+          __syncwarp();
           rl.next();
           ro.next();
         }
-        tc_commit(&tmem_full_bar[set]);  // accumulators complete
+        if (elect_one()) tc_commit(&tmem_full_bar[set]);  // accumulators complete
+        __syncwarp();
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -454,7 +474,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 // TMEM columns: [0,256) accumulators (2 sets x G pairs of (main | small)), [256,512) A ring.
 template <int N>
 __global__ void __launch_bounds__(kGemmThreadsTmemA, 1)
-gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ GemmParams p) {
+gemm_3xtf32_tmemA_kernel(const __grid_constant__ GemmParams p) {
   static_assert(N == 32 || N == 64 || N == 128, "tensor-memory A variant: N <= 128");
   constexpr int kTileX = N * kBK * 4;
   constexpr int kLandSlot = kTileA + 2 * kTileX;   // raw weight tile | X_hi | X_lo
@@ -492,7 +512,6 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
       mbar_init(&tmem_empty_bar[s], 4);
     }
     mbar_fence_init();
-    tmap_prefetch(&tmW);
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -538,7 +557,7 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
       int ahead = 0;
       while (!a.done() && ahead < DL) {
         mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
-        tma_load_2d(land + (size_t)ra.i * kLandSlot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
+        bulk_g2s(land + (size_t)ra.i * kLandSlot, p.Wt + ((size_t)(a.mt) * p.kblocks + (a.kb)) * (kBM * kBK), kTileA, &land_full[ra.i]);
         ra.next();
         a.next();
         ++ahead;
@@ -551,11 +570,14 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
         rx.next();
         x.next();
       }
+      int ord = ahead;
       while (!a.done()) {
         mbar_wait(&land_empty[ra.i], ra.ph ^ 1);
+        if (p.dbg && blockIdx.x == 0 && ord < 256) p.dbg[ord * 8 + 0] = clock64();
+        ++ord;
         unsigned char* slot = land + (size_t)ra.i * kLandSlot;
         mbar_arrive_expect_tx(&land_full[ra.i], kLandSlot);
-        tma_load_2d(slot, &tmW, a.kb * kBK, a.mt * kBM, &land_full[ra.i]);
+        bulk_g2s(slot, p.Wt + ((size_t)(a.mt) * p.kblocks + (a.kb)) * (kBM * kBK), kTileA, &land_full[ra.i]);
         bulk_g2s(slot + kTileA, p.Xh + ((size_t)(a.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[ra.i]);
         bulk_g2s(slot + kTileA + kTileX, p.Xl + ((size_t)(a.kb) * p.npad + p.n0) * kBK, kTileX, &land_full[ra.i]);
         ra.next();
@@ -563,10 +585,10 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer: A from tensor memory ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer: A from tensor memory (whole warp, one elected lane issues) ----
+    {
       Ring rl(DL), ro(kASlots);
-      int li = 0;
+      int li = 0, mord = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
         const int split = it / p.tiles_m;
         const int kb0 = (int)(((long long)p.kblocks * split) / p.S);
@@ -581,6 +603,7 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
           const uint32_t d_small = d_main + (uint32_t)N;
           const uint32_t acc0 = kk >= G ? 1u : 0u;
           mbar_wait(&a_full[ro.i], ro.ph);  // w_hi / w_lo of this k-block are in TMEM (=> tile landed)
+          if (p.dbg && blockIdx.x == 0 && mord < 256 && lane == 0) p.dbg[mord * 8 + 4] = clock64();
           tc_fence_after();
           unsigned char* ls = land + (size_t)rl.i * kLandSlot;
           const uint64_t dXh = umma_desc_sw128(ls + kTileA);
@@ -590,23 +613,32 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
           for (int k = 0; k < kBK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
             const uint32_t acc = k != 0 ? 1u : acc0;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_main),
-                "r"(a_hi + (uint32_t)(k * 8)), "l"(dXh + adv), "r"(kIdesc2), "r"(acc)
-                : "memory");  // w_hi * [x_hi ; x_lo]
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_small),
-                "r"(a_lo + (uint32_t)(k * 8)), "l"(dXh + adv), "r"(kIdesc), "r"(1u)
-                : "memory");  // w_lo * x_hi
+            if (elect_one()) {
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_main),
+                  "r"(a_hi + (uint32_t)(k * 8)), "l"(dXh + adv), "r"(kIdesc2), "r"(acc)
+                  : "memory");  // w_hi * [x_hi ; x_lo]
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_small),
+                  "r"(a_lo + (uint32_t)(k * 8)), "l"(dXh + adv), "r"(kIdesc), "r"(1u)
+                  : "memory");  // w_lo * x_hi
+            }
+            __syncwarp();
           }
-          tc_commit(&land_empty[rl.i]);
-          tc_commit(&a_empty[ro.i]);
+          if (elect_one()) {
+            tc_commit(&land_empty[rl.i]);
+            tc_commit(&a_empty[ro.i]);
+          }
+          __syncwarp();
+          if (p.dbg && blockIdx.x == 0 && mord < 256 && lane == 0) p.dbg[mord * 8 + 5] = clock64();
+          ++mord;
           rl.next();
           ro.next();
         }
-        tc_commit(&tmem_full_bar[set]);
+        if (elect_one()) tc_commit(&tmem_full_bar[set]);
+        __syncwarp();
       }
     }
   } else if ((warp >= 4 && warp < 8) || warp >= 12) {
@@ -624,8 +656,11 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
       const int ls = n % DL, lph = (n / DL) & 1;
       const int as = n % kASlots, aph = (n / kASlots) & 1;
       mbar_wait(&a_empty[as], aph ^ 1);
+      const bool rec = p.dbg && blockIdx.x == 0 && n < 256 && (warp & 3) == 0 && lane == 0;
+      if (rec) p.dbg[n * 8 + 1] = clock64();
       tc_fence_after();
       mbar_wait(&land_full[ls], lph);
+      if (rec) p.dbg[n * 8 + 2] = clock64();
       const unsigned char* tile = land + (size_t)ls * kLandSlot + (size_t)row * 128;
       uint32_t hi[32], lo[32];
 #pragma unroll
@@ -644,6 +679,7 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[as]);
+      if (rec) p.dbg[n * 8 + 3] = clock64();
     }
   } else if (warp >= 8 && warp < 12) {
     // ---------------- epilogue (same as above) ----------------
@@ -699,6 +735,24 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
                  : "memory");
+  }
+}
+
+// Row-major [M][K] -> tile-major pre-swizzled copy used by the GEMMs (one-time, at first
+// batched use; partial tiles are zero-padded).  One thread per 16-byte chunk.
+__global__ void __launch_bounds__(256) tile_major_kernel(const float* __restrict__ W, float* __restrict__ Wt, int M,
+                                                         int K, int tiles_m, int kblocks) {
+  const size_t n_chunks = (size_t)tiles_m * kblocks * (kBM * kBK / 4);
+  for (size_t q = (size_t)blockIdx.x * 256 + threadIdx.x; q < n_chunks; q += (size_t)gridDim.x * 256) {
+    const size_t tile = q / (kBM * kBK / 4);
+    const int within = (int)(q - tile * (kBM * kBK / 4));
+    const int r = within >> 3, pc = within & 7;
+    const int c = pc ^ (r & 7);                      // logical chunk stored at physical position pc
+    const int mt = (int)(tile / kblocks), kb = (int)(tile - (size_t)mt * kblocks);
+    const int row = mt * kBM + r, col = kb * kBK + c * 4;
+    float4 v = f4_zero();
+    if (row < M && col < K) v = *reinterpret_cast<const float4*>(W + (size_t)row * K + col);
+    reinterpret_cast<float4*>(Wt)[q] = v;
   }
 }
 

@@ -91,6 +91,11 @@ struct l2b_ctx {
   int pf_cap = 0;
   // batched tensor-core path: pre-split activations [256*groups][D or F], partial sums
   float *XhD = nullptr, *XlD = nullptr, *XhF = nullptr, *XlF = nullptr, *P = nullptr;
+  long long* d_dbg = nullptr; // kernel timeline buffer (debug option "gemm_timeline")
+  int dbg_arm = 0;
+  float* Wt = nullptr;       // tile-major copy of every projection (built at first batched use)
+  bool wt_dirty = true;      // weights changed since the copy was built
+  std::vector<size_t> wt_off; // float offsets: per layer {qkv, wo, w13, w2}, then cls
   size_t P_floats = 0;
   int Bpad = 0, Smax = 8;
   std::map<std::pair<const void*, int>, CUtensorMap> tmaps;  // key: (operand base, box rows)
@@ -343,19 +348,18 @@ int pick_splits(const l2b_ctx* c, int M, int K, int B) {
   return best_s;
 }
 
-int launch_gemm(l2b_ctx* c, int kclass, const float* W, int M, int K, const float* Xh, const float* Xl,
+int launch_gemm(l2b_ctx* c, int kclass, const float* Wt, int M, int K, const float* Xh, const float* Xl,
                 int B, int* S_out, cudaStream_t st) {
   const int S = pick_splits(c, M, K, B);
   *S_out = S;
   for (int n0 = 0; n0 < B; n0 += 256) {
     const int cols = (B - n0) < 256 ? (B - n0) : 256;
     const int N = gemm_n_for(cols);
-    const CUtensorMap* tW;
-    int rc = get_tmap(c, W, M, K, kBM, &tW);
-    if (rc) return rc;
+    int rc = 0;
     GemmParams g;
     g.P = c->P;
-    g.Xh = Xh; g.Xl = Xl; g.npad = c->Bpad;
+    g.Wt = Wt; g.Xh = Xh; g.Xl = Xl; g.npad = c->Bpad;
+    g.dbg = (c->dbg_arm && kclass == L2B_K_GEMM_W13) ? c->d_dbg : nullptr;
     g.M = M; g.K = K; g.S = S; g.B = B; g.n0 = n0;
     g.tiles_m = (M + kBM - 1) / kBM;
     g.kblocks = (K + kBK - 1) / kBK;
@@ -384,8 +388,7 @@ int launch_gemm(l2b_ctx* c, int kclass, const float* W, int M, int K, const floa
     }
     int items = g.tiles_m * S;
     const int grid = items < c->num_sms ? items : c->num_sms;
-    CUtensorMap a = *tW;
-    void* args[] = {&a, &g};
+    void* args[] = {&g};
     rc = launch(c, kclass, fn, dim3(grid), dim3(threads), smem_bytes, 1, args, st);
     if (rc) return rc;
   }
@@ -403,6 +406,49 @@ struct BatchView {
   int cls_mode;        // 0: classifier for every entry (batched decode); 1: last entry only;
                        // 2: none (a prefill chunk that is not the last one)
 };
+
+size_t tile_major_floats(int M, int K) {
+  return (size_t)((M + kBM - 1) / kBM) * ((K + kBK - 1) / kBK) * (kBM * kBK);
+}
+
+// Builds (or refreshes) the tile-major weight copy the GEMMs stream.  Not capturable: called
+// before a graph capture / launch sequence starts.
+int ensure_tc_weights(l2b_ctx* c) {
+  if (c->Wt && !c->wt_dirty) return 0;
+  const int D = c->D, F = c->F, V = c->V, L = c->L;
+  if (!c->Wt) {
+    c->wt_off.clear();
+    size_t off = 0;
+    for (int l = 0; l < L; ++l) {
+      c->wt_off.push_back(off); off += tile_major_floats(3 * D, D);
+      c->wt_off.push_back(off); off += tile_major_floats(D, D);
+      c->wt_off.push_back(off); off += tile_major_floats(2 * F, D);
+      c->wt_off.push_back(off); off += tile_major_floats(D, F);
+    }
+    c->wt_off.push_back(off); off += tile_major_floats(V, D);
+    int rc = dev_alloc(c, &c->Wt, off, false);
+    if (rc) return rc;
+  }
+  auto conv = [&](const float* W, size_t off, int M, int K) -> int {
+    const int tiles_m = (M + kBM - 1) / kBM, kblocks = (K + kBK - 1) / kBK;
+    tile_major_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(W, c->Wt + off, M, K, tiles_m, kblocks);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, L2B_ECUDA, "tile_major_kernel: %s", cudaGetErrorString(e));
+    return 0;
+  };
+  int rc = 0;
+  for (int l = 0; l < L && !rc; ++l) {
+    rc = conv(c->wqkv + (size_t)l * 3 * D * D, c->wt_off[4 * l + 0], 3 * D, D);
+    if (!rc) rc = conv(c->wo + (size_t)l * D * D, c->wt_off[4 * l + 1], D, D);
+    if (!rc) rc = conv(c->w13 + (size_t)l * 2 * F * D, c->wt_off[4 * l + 2], 2 * F, D);
+    if (!rc) rc = conv(c->w2 + (size_t)l * D * F, c->wt_off[4 * l + 3], D, F);
+  }
+  if (!rc) rc = conv(c->wcls, c->wt_off[4 * L], V, D);
+  if (rc) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->wt_dirty = false;
+  return 0;
+}
 
 int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v) {
   const int D = c->D, F = c->F, hs = c->hs, H = c->H, V = c->V;
@@ -428,7 +474,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
   if (rc) return rc;
   const int cs = auto_cluster(c, B);
   for (int l = 0; l < c->L; ++l) {
-    rc = launch_gemm(c, L2B_K_GEMM_QKV, c->wqkv + (size_t)l * 3 * D * D, 3 * D, D, c->XhD, c->XlD, B, &S, st);
+    rc = launch_gemm(c, L2B_K_GEMM_QKV, c->Wt + c->wt_off[4 * l + 0], 3 * D, D, c->XhD, c->XlD, B, &S, st);
     if (rc) return rc;
     {
       BatQkvParams q;
@@ -463,11 +509,11 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
                   args, st);
       if (rc) return rc;
     }
-    rc = launch_gemm(c, L2B_K_GEMM_WO, c->wo + (size_t)l * D * D, D, D, c->XhD, c->XlD, B, &S, st);
+    rc = launch_gemm(c, L2B_K_GEMM_WO, c->Wt + c->wt_off[4 * l + 1], D, D, c->XhD, c->XlD, B, &S, st);
     if (rc) return rc;
     rc = resid_rms(c->P, S, nullptr, c->rms_ffn + (size_t)l * D);
     if (rc) return rc;
-    rc = launch_gemm(c, L2B_K_GEMM_W13, c->w13 + (size_t)l * 2 * F * D, 2 * F, D, c->XhD, c->XlD, B, &S, st);
+    rc = launch_gemm(c, L2B_K_GEMM_W13, c->Wt + c->wt_off[4 * l + 2], 2 * F, D, c->XhD, c->XlD, B, &S, st);
     if (rc) return rc;
     {
       BatSwigluParams w;
@@ -478,7 +524,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
                   st);
       if (rc) return rc;
     }
-    rc = launch_gemm(c, L2B_K_GEMM_W2, c->w2 + (size_t)l * D * F, D, F, c->XhF, c->XlF, B, &S, st);
+    rc = launch_gemm(c, L2B_K_GEMM_W2, c->Wt + c->wt_off[4 * l + 3], D, F, c->XhF, c->XlF, B, &S, st);
     if (rc) return rc;
     rc = resid_rms(c->P, S, nullptr, l + 1 < c->L ? c->rms_att + (size_t)(l + 1) * D : c->rms_final);
     if (rc) return rc;
@@ -501,7 +547,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
     p.evict_first = c->weight_bytes > (size_t)100 * 1024 * 1024;
     return launch_gemv(c, L2B_K_CLS, p, 1, st);
   }
-  rc = launch_gemm(c, L2B_K_GEMM_CLS, c->wcls, V, D, c->XhD, c->XlD, B, &S, st);
+  rc = launch_gemm(c, L2B_K_GEMM_CLS, c->Wt + c->wt_off[4 * c->L], V, D, c->XhD, c->XlD, B, &S, st);
   if (rc) return rc;
   {
     BatLogitsParams g;
@@ -875,6 +921,10 @@ bool use_mega(const l2b_ctx* c, int B) {
 // Events ev0/ev1 bracket the device work on the ctx stream.
 int run_steps(l2b_ctx* c, int B, int n_steps) {
   const int64_t l0 = c->launch_counter;
+  if (c->tp_size == 1 && c->opt.tc_min_batch > 0 && B >= c->opt.tc_min_batch && c->P != nullptr) {
+    int rc = ensure_tc_weights(c);  // tile-major weight copy of the tensor-core path
+    if (rc) return rc;
+  }
   if (use_mega(c, B)) {
     CU(c, cudaEventRecord(c->ev0, c->stream));
     int rc = launch_mega(c, n_steps, c->stream);
@@ -1171,7 +1221,7 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
   float* fl[] = {c->tok_emb, c->rms_att, c->wqkv, c->wo, c->rms_ffn, c->w13, c->w2, c->rms_final,
                  c->fcr, c->fci, c->shared_cls ? nullptr : c->wcls, c->x, c->xb, c->q, c->hb,
                  c->logits, c->kc, c->vc, c->blk_val, c->XhD, c->XlD, c->XhF, c->XlF, c->P,
-                 c->pf_x, c->pf_xb, c->pf_q};
+                 c->pf_x, c->pf_xb, c->pf_q, c->Wt};
   for (float* p : fl)
     if (p) cudaFree(p);
   int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar};
@@ -1259,6 +1309,7 @@ L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float
   // caller may free `host` on return and the next step sees the new contents
   CU(c, cudaStreamSynchronize(c->stream));
   c->uploaded[(size_t)tensor_id * c->L + layer] = 1;
+  c->wt_dirty = true;
   return L2B_OK;
 }
 
@@ -1332,7 +1383,7 @@ L2B_API int l2b_load_checkpoint(l2b_ctx* c, const char* path, double* seconds_ou
         used[slot] = true;
         slot ^= 1;
       }
-      if (!rc) c->uploaded[(size_t)t * c->L + l] = 1;
+      if (!rc) { c->uploaded[(size_t)t * c->L + l] = 1; c->wt_dirty = true; }
       file_off += pl.expect * sizeof(float);
     }
     if (rc) break;
@@ -1449,6 +1500,8 @@ L2B_API int l2b_prefill(l2b_ctx* c, int32_t seq, int32_t n_tokens, const int32_t
   CU(c, cudaSetDevice(c->device));
   const int cap = n_tokens < 256 ? (n_tokens < 32 ? 32 : n_tokens) : 256;
   rc = ensure_prefill(c, cap);
+  if (rc) return rc;
+  rc = ensure_tc_weights(c);
   if (rc) return rc;
   const size_t kv_seq = (size_t)c->H * c->steps * c->hs;
   const int64_t l0 = c->launch_counter;
@@ -1597,6 +1650,14 @@ L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer
   return L2B_OK;
 }
 
+L2B_API int l2b_debug_timeline(l2b_ctx* c, int64_t* out, uint64_t n) {
+  if (!c || !out || !c->d_dbg) return L2B_EINVAL;
+  if (n > 256 * 8) n = 256 * 8;
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaMemcpy(out, c->d_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  return L2B_OK;
+}
+
 L2B_API int l2b_reset(l2b_ctx* c) {
   if (!c) return L2B_EINVAL;
   CU(c, cudaSetDevice(c->device));
@@ -1637,6 +1698,12 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.attn_prefetch = v != 0;
   } else if (k == "mega") {
     o.mega = v != 0;
+  } else if (k == "gemm_timeline") {
+    if (v && !c->d_dbg) {
+      if (cudaMalloc((void**)&c->d_dbg, 256 * 8 * sizeof(long long)) != cudaSuccess) return fail(c, L2B_ENOMEM, "dbg");
+      cudaMemset(c->d_dbg, 0, 256 * 8 * sizeof(long long));
+    }
+    c->dbg_arm = v != 0;
   } else if (k == "tc_tmem_a") {
     o.tc_tmem_a = v != 0;
   } else if (k == "tc_rewrite_hi") {
