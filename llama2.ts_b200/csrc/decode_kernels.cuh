@@ -636,6 +636,7 @@ struct AttnParams {
   float* xh;
   float* xl;
   int x_npad;
+  int nbatch;        // attn_warp_kernel: number of batch entries
   // attention is latency-bound and leaves HBM idle: meanwhile pull the NEXT kernel's weights
   // (wo of this layer) into L2
   const unsigned char* pf_ptr;
@@ -866,6 +867,101 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
     }
   }
   cluster_sync_all();  // keep every CTA's shared memory alive until rank 0 has read it
+}
+
+// Batched attention: ONE WARP per (sequence, head) (llama2.ts:244-267).  With hundreds of
+// independent (sequence, head) pairs there is no need to split one head over a cluster: the
+// cluster kernel above spends ~8 us of latency per CTA (mbarrier setup, TMA round trips, four
+// cluster barriers) on ~70 KB of cache, which made attention 19 % of a 256-sequence step.
+// Here a warp streams its head's K rows then V rows with coalesced 512-byte loads, several
+// rows in flight, no block-level synchronisation; the softmax keeps the reference's two-pass
+// form (global max, f32-rounded exponentials, f64 sum).  Scores live in shared memory.
+constexpr int kAttnWarpThreads = 256;
+constexpr int kAttnWarpRows = 8;   // cache rows in flight per warp (head_size <= 128: one float4 per lane)
+__global__ void __launch_bounds__(kAttnWarpThreads) attn_warp_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(16) float attn_warp_sc[];  // [warps][sc_cap]
+  griddep_launch_dependents();
+  griddep_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * (kAttnWarpThreads / 32) + warp;  // (b, h)
+  if (item >= p.nbatch * p.H) return;
+  const int b = item / p.H, h = item - b * p.H;
+  const int hs = p.hs, hs4 = hs >> 2;
+  const bool on = lane < hs4;
+  float* sc = attn_warp_sc + (size_t)warp * p.sc_cap;
+  const int pos = ld_act_i32(p.posp + b);
+  const int n_t = pos + 1;
+  const size_t head_off = (size_t)b * (size_t)p.kv_b_stride + ((size_t)h * p.steps) * hs;
+  const float4* k4 = reinterpret_cast<const float4*>(p.kc + head_off) + lane;
+  const float4* v4 = reinterpret_cast<const float4*>(p.vc + head_off) + lane;
+  const float4 qv = on ? ld_act4(reinterpret_cast<const float4*>(p.q + (size_t)b * p.q_stride + (size_t)h * hs) + lane)
+                       : f4_zero();
+  const double sqrt_hs = sqrt((double)hs);
+
+  // pass 1: scores
+  float lmax = -INFINITY;
+  for (int t0 = 0; t0 < n_t; t0 += kAttnWarpRows) {
+    float4 kr[kAttnWarpRows];
+#pragma unroll
+    for (int u = 0; u < kAttnWarpRows; ++u)
+      kr[u] = (on && t0 + u < n_t) ? __ldcg(k4 + (size_t)(t0 + u) * hs4) : f4_zero();
+#pragma unroll
+    for (int u = 0; u < kAttnWarpRows; ++u) {
+      double d = fma((double)qv.x, (double)kr[u].x, 0.0);
+      d = fma((double)qv.y, (double)kr[u].y, d);
+      d = fma((double)qv.z, (double)kr[u].z, d);
+      d = fma((double)qv.w, (double)kr[u].w, d);
+      d = warp_sum_f64(d);
+      if (t0 + u < n_t) {
+        const float sv = (float)(d / sqrt_hs);
+        if (lane == 0) sc[t0 + u] = sv;
+        lmax = fmaxf(lmax, sv);
+      }
+    }
+  }
+  __syncwarp();
+  // softmax (llama2.ts:181-194)
+  double lsum = 0.0;
+  for (int t = lane; t < n_t; t += 32) {
+    const float e = (float)exp((double)sc[t] - (double)lmax);
+    sc[t] = e;
+    lsum += (double)e;
+  }
+  lsum = warp_sum_f64(lsum);
+  __syncwarp();
+  for (int t = lane; t < n_t; t += 32) sc[t] = (float)((double)sc[t] / lsum);
+  __syncwarp();
+  // pass 2: weighted sum of the value rows
+  float4 acc = f4_zero();
+  for (int t0 = 0; t0 < n_t; t0 += kAttnWarpRows) {
+    float4 vr[kAttnWarpRows];
+#pragma unroll
+    for (int u = 0; u < kAttnWarpRows; ++u)
+      vr[u] = (on && t0 + u < n_t) ? __ldcg(v4 + (size_t)(t0 + u) * hs4) : f4_zero();
+#pragma unroll
+    for (int u = 0; u < kAttnWarpRows; ++u) {
+      const float a = (t0 + u < n_t) ? sc[t0 + u] : 0.f;
+      acc.x = fmaf(a, vr[u].x, acc.x);
+      acc.y = fmaf(a, vr[u].y, acc.y);
+      acc.z = fmaf(a, vr[u].z, acc.z);
+      acc.w = fmaf(a, vr[u].w, acc.w);
+    }
+  }
+  if (on) {
+    const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+    const size_t o = (size_t)b * p.xb_stride + p.xb_off + (size_t)h * hs + 4 * lane;
+    *reinterpret_cast<float4*>(p.xb + o) = acc;
+    if (p.xh != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = h * hs + 4 * lane + e;
+        const size_t xi = ((size_t)(j >> 5) * p.x_npad + b) * 32 + ((((j >> 2) & 7) ^ (b & 7)) << 2) + (j & 3);
+        const float hi = __uint_as_float((__float_as_uint(vals[e]) + 0x1000u) & 0xFFFFE000u);
+        p.xh[xi] = hi;
+        p.xl[xi] = vals[e] - hi;
+      }
+    }
+  }
 }
 
 // Tensor-parallel step epilogue (one warp): waits for every rank's classifier slice, picks

@@ -45,6 +45,8 @@ struct Options {
   int tc_min_batch = 5;  // batches >= this run the tcgen05 GEMM path (0 = never)
   int tc_splits = 0;     // 0 = auto k-split per GEMM
   int tc_rewrite_hi = 0; // see GemmParams::rewrite_hi
+  int attn_warp = 2048;  // batched path: one-warp-per-(sequence, head) attention kernel when there are at
+                         // least this many (sequence, head) pairs (0 = never); below, the cluster kernel
   int tc_tmem_a = 1;     // N <= 128: weight operand in tensor memory (gemm_3xtf32_tmemA_kernel)
   int l2_prefetch = 262144;  // bytes per CTA prefetched into L2 before griddep_wait (0 = off)
   int attn_prefetch = 0;     // attention kernel prefetches the wo weights into L2 (measured net-negative: it
@@ -503,10 +505,19 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
       a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
       a.tp_size = 1;
       a.xh = c->XhD; a.xl = c->XlD; a.x_npad = c->Bpad;
-      const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
-      rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B), dim3(kAttnThreads), smem, cs,
-                  args, st);
+      if (c->opt.attn_warp && hs <= 128 && B * H >= c->opt.attn_warp) {
+        // one warp per (entry, head): throughput kernel for many independent pairs
+        a.sc_cap = (c->steps + 3) & ~3;
+        a.nbatch = B;
+        const int wpc = kAttnWarpThreads / 32;
+        rc = launch(c, L2B_K_ATTN, (const void*)attn_warp_kernel, dim3((B * H + wpc - 1) / wpc),
+                    dim3(kAttnWarpThreads), (size_t)wpc * a.sc_cap * 4, 1, args, st);
+      } else {
+        const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
+        rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B), dim3(kAttnThreads), smem, cs,
+                    args, st);
+      }
       if (rc) return rc;
     }
     rc = launch_gemm(c, L2B_K_GEMM_WO, c->Wt + c->wt_off[4 * l + 1], D, D, c->XhD, c->XlD, B, &S, st);
@@ -1704,6 +1715,8 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
       cudaMemset(c->d_dbg, 0, 256 * 8 * sizeof(long long));
     }
     c->dbg_arm = v != 0;
+  } else if (k == "attn_warp") {
+    o.attn_warp = v < 0 ? 0 : v;
   } else if (k == "tc_tmem_a") {
     o.tc_tmem_a = v != 0;
   } else if (k == "tc_rewrite_hi") {
