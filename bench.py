@@ -524,6 +524,33 @@ def main():
             except Exception as e:  # never lose the headline line to a side measurement
                 others[name] = {"error": str(e)}
         line["others"] = others
+        try:   # temperature / top-p sampling on the device vs logits to the host
+            h4 = pkg.synth.header("stories15M")
+            st4, _ = run_workload(pkg, "stories15M", local_rank, 200, 8, args.seed)
+            c4 = st4["ctx"]
+            H = pkg.host
+            res = {}
+            for name in ("host_sampler", "device_sampler"):
+                c4.reset()
+                rng, tok4, lg4 = H.Rng(1), 1, np.empty(32000, dtype=np.float32)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for p4 in range(200):
+                    if name == "device_sampler":
+                        tok4 = c4.forward_sample(tok4, p4, 0.8, 0.9, rng.random_f32())
+                    else:
+                        c4.forward(tok4, p4, lg4)
+                        lg4[:] = (lg4.astype(np.float64) / 0.8).astype(np.float32)
+                        H.softmax(lg4, 0, 32000)
+                        tok4 = H.sample_topp(lg4, 0.9, rng)
+                    tok4 = tok4 if tok4 != 1 else 2
+                res[name + "_tokens_per_s"] = 200 / (time.perf_counter() - t0)
+            res["note"] = ("stories15M, -t 0.8 -p 0.9, 200 tokens end to end: l2b_forward + the host mirror's "
+                           "numpy sampler (128 KB of logits per token) vs l2b_forward_sample (4 bytes per token)")
+            line["sampling"] = res
+            c4.close()
+        except Exception as e:
+            line["sampling"] = {"error": str(e)}
         try:   # checkpoint loader fast path vs the reference-order per-tensor reads
             import tempfile
             h3 = pkg.synth.header("stories110M")

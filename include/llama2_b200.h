@@ -108,6 +108,19 @@ int l2b_forward(l2b_ctx* ctx, int32_t token, int32_t pos, float* logits_out);
  * first maximum wins) computed on the device -- the `-t 0` path, llama2.ts:478. */
 int l2b_forward_argmax(l2b_ctx* ctx, int32_t token, int32_t pos, int32_t* next_out);
 
+/* Device-side sampling.  One decode step followed by what
+ * the host does at llama2.ts:476-494 -- logits /= temperature, softmax, then sample()
+ * (topp <= 0 or >= 1, llama2.ts:368-376) or sample_topp() (llama2.ts:378-394, including its
+ * exclusive `i < lastIdx` walk and the fallback to token 0) -- with only the chosen token
+ * coming back.  rand01 is the host's random_f32() for this token (the reference draws exactly
+ * one per sampled token, :370/:388), so the xorshift stream stays on the host, unchanged.
+ * temperature == 0 is the argmax path.  temperature/topp are doubles like JS numbers.       */
+int l2b_forward_sample(l2b_ctx* ctx, int32_t token, int32_t pos, double temperature, double topp,
+                       float rand01, int32_t* next_out);
+/* The same sampler on caller-supplied logits (vocab floats, host); for tests and tools.   */
+int l2b_sample_logits(l2b_ctx* ctx, const float* logits_host, double temperature, double topp,
+                      float rand01, int32_t* next_out);
+
 /* B independent sequences advance one step each (sequence b uses RunState b).
  * tokens[b], pos[b] as above; logits_out (B*vocab floats, host) may be NULL;
  * argmax_out (B ints, host) may be NULL.                                       */

@@ -5,7 +5,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "l2b.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("l2b.cu", "common.cuh", "decode_kernels.cuh", "batch_gemm.cuh", "mega_kernel.cuh")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("l2b.cu", "common.cuh", "decode_kernels.cuh", "batch_gemm.cuh", "mega_kernel.cuh", "sampler.cuh")] + [
     os.path.join(HERE, "..", "include", "llama2_b200.h")]
 OUT = os.path.join(HERE, "libllama2_b200.so")
 

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "l2b_forward": (C.c_int, [_p, _i32, _i32, _p]),
     "l2b_forward_argmax": (C.c_int, [_p, _i32, _i32, C.POINTER(_i32)]),
     "l2b_forward_batch": (C.c_int, [_p, _i32, _p, _p, _p, _p]),
+    "l2b_forward_sample": (C.c_int, [_p, _i32, _i32, C.c_double, C.c_double, _f32, C.POINTER(_i32)]),
+    "l2b_sample_logits": (C.c_int, [_p, _p, C.c_double, C.c_double, _f32, C.POINTER(_i32)]),
     "l2b_generate_greedy": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _p]),
     "l2b_prefill": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, C.POINTER(_i32)]),
     "l2b_last_device_ms": (_f32, [_p]),
@@ -199,6 +201,21 @@ class Context:
     def forward_argmax(self, token, pos):
         nxt = _i32(0)
         self._check(self.lib.dll.l2b_forward_argmax(self._h, token, pos, C.byref(nxt)))
+        return int(nxt.value)
+
+    def forward_sample(self, token, pos, temperature, topp, rand01):
+        """One step + temperature/softmax/sampler on the device; rand01 = the host's random_f32()."""
+        nxt = _i32(0)
+        self._check(self.lib.dll.l2b_forward_sample(self._h, token, pos, float(temperature), float(topp),
+                                                    float(rand01), C.byref(nxt)))
+        return int(nxt.value)
+
+    def sample_logits(self, logits, temperature, topp, rand01):
+        logits = np.ascontiguousarray(logits, dtype=np.float32)
+        assert logits.size == self.vocab_size
+        nxt = _i32(0)
+        self._check(self.lib.dll.l2b_sample_logits(self._h, _ptr(logits), float(temperature), float(topp),
+                                                   float(rand01), C.byref(nxt)))
         return int(nxt.value)
 
     def forward_batch(self, tokens, pos, want_logits=True, want_argmax=True):

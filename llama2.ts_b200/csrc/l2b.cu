@@ -25,6 +25,7 @@
 #include "batch_gemm.cuh"
 #include "decode_kernels.cuh"
 #include "mega_kernel.cuh"
+#include "sampler.cuh"
 
 #define L2B_API extern "C" __attribute__((visibility("default")))
 
@@ -87,6 +88,8 @@ struct l2b_ctx {
   int* blk_idx = nullptr;
   int *d_forced = nullptr, *d_out = nullptr;
   unsigned* d_bar = nullptr;  // grid barrier words of the persistent kernel
+  float* samp_f = nullptr;    // device sampler scratch: probs | cand_p | sort_p  (3 x vocab)
+  int* samp_i = nullptr;      //                         cand_i | sort_i          (2 x vocab)
   // prompt prefill scratch (l2b_prefill): activations of `pf_cap` positions of one sequence
   float *pf_x = nullptr, *pf_xb = nullptr, *pf_q = nullptr;
   int *d_pfctl = nullptr, *h_pfctl = nullptr;
@@ -1176,6 +1179,8 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     c->P_floats = (size_t)c->Smax * sB * Mmax;
   }
   TRY(dev_alloc(c, &c->d_bar, 4, true));
+  TRY(dev_alloc(c, &c->samp_f, 4 * sV, true));
+  TRY(dev_alloc(c, &c->samp_i, 2 * sV, true));
   TRY(dev_alloc(c, &c->d_forced, (size_t)max_steps * sB, true));
   TRY(dev_alloc(c, &c->d_out, (size_t)max_steps * sB, true));
 #undef TRY
@@ -1235,7 +1240,7 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
                  c->pf_x, c->pf_xb, c->pf_q, c->Wt};
   for (float* p : fl)
     if (p) cudaFree(p);
-  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar};
+  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->samp_i, (int*)c->samp_f};
   for (int* p : il)
     if (p) cudaFree(p);
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -1546,6 +1551,60 @@ L2B_API int l2b_prefill(l2b_ctx* c, int32_t seq, int32_t n_tokens, const int32_t
   if (logits_out) memcpy(logits_out, c->h_logits, sizeof(float) * c->V);
   if (argmax_out) *argmax_out = c->h_out[0];
   if (pos0 + n_tokens > c->n_run[seq]) c->n_run[seq] = pos0 + n_tokens;
+  return L2B_OK;
+}
+
+// Device sampler on `logits` (device pointer, vocab floats); result lands in d_dev[1].
+static int enqueue_sampler(l2b_ctx* c, const float* logits, double temperature, double topp, double rand01) {
+  SampleParams sp;
+  memset(&sp, 0, sizeof sp);
+  sp.logits = logits; sp.V = c->V;
+  sp.temperature = temperature; sp.topp = topp; sp.rand01 = rand01;
+  sp.probs = c->samp_f; sp.cand_p = c->samp_f + c->V; sp.sort_p = c->samp_f + 2 * (size_t)c->V;
+  sp.cand_i = c->samp_i; sp.sort_i = c->samp_i + c->V;
+  sp.next = c->d_dev + 1;
+  void* args[] = {&sp};
+  return launch(c, L2B_K_CLS, (const void*)sample_kernel, dim3(1), dim3(kSampThreads), 0, 1, args, c->stream);
+}
+
+L2B_API int l2b_forward_sample(l2b_ctx* c, int32_t token, int32_t pos, double temperature, double topp,
+                               float rand01, int32_t* next_out) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!next_out) return fail(c, L2B_EINVAL, "null next_out");
+  if (temperature == 0.0) return l2b_forward_argmax(c, token, pos, next_out);  // llama2.ts:476-478
+  CU(c, cudaSetDevice(c->device));
+  rc = stage_inputs(c, 1, &token, &pos, 0, 0, 0, 1);
+  if (rc) return rc;
+  rc = run_steps(c, 1, 1);
+  if (rc) return rc;
+  rc = enqueue_sampler(c, c->logits, temperature, topp, (double)rand01);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_out, c->d_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  rc = finish(c);
+  if (rc) return rc;
+  *next_out = c->h_out[0];
+  mark_run(c, 1, &pos, 1);
+  return L2B_OK;
+}
+
+L2B_API int l2b_sample_logits(l2b_ctx* c, const float* logits_host, double temperature, double topp, float rand01,
+                              int32_t* next_out) {
+  if (!c) return L2B_EINVAL;
+  if (!logits_host || !next_out) return fail(c, L2B_EINVAL, "null argument");
+  if (temperature == 0.0) return fail(c, L2B_EINVAL, "temperature 0 is the argmax path (l2b_forward_argmax)");
+  CU(c, cudaSetDevice(c->device));
+  float* dl = c->samp_f + 3 * (size_t)c->V;
+  CU(c, cudaMemcpyAsync(dl, logits_host, sizeof(float) * c->V, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(c->ev0, c->stream));
+  int rc = enqueue_sampler(c, dl, temperature, topp, (double)rand01);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_out, c->d_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  rc = finish(c);
+  if (rc) return rc;
+  *next_out = c->h_out[0];
   return L2B_OK;
 }
 

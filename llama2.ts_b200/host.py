@@ -198,7 +198,7 @@ def sample_topp(logits, topp, rng):
 # generate loop (llama2.ts:460-511)
 
 def generate(config, weights, state, steps, prompt_tokens, temperature, topp, rng, on_token=None,
-             device_greedy=False, prefill=False):
+             device_greedy=False, prefill=False, device_sampler=False):
     """The `while (pos < steps)` loop.  Returns (tokens, tok_per_s).
     device_greedy=True keeps the whole -t 0 loop on the device (l2b_generate_greedy):
     same tokens, no per-token round trip."""
@@ -239,8 +239,14 @@ def generate(config, weights, state, steps, prompt_tokens, temperature, topp, rn
         pos = n_prompt
         start = time.time()
     while pos < steps:
-        transformer(token, pos, config, state, weights)          # llama2.ts:468
-        if pos < n_prompt:
+        if device_sampler and pos >= n_prompt and temperature != 0.0:
+            # llama2.ts:468 + :481-494 in one call; the random number is still drawn here
+            nxt = weights.ctx.forward_sample(token, pos, temperature, topp, rng.random_f32())
+        else:
+            transformer(token, pos, config, state, weights)      # llama2.ts:468
+        if device_sampler and pos >= n_prompt and temperature != 0.0:
+            pass
+        elif pos < n_prompt:
             nxt = int(prompt_tokens[pos])
         elif temperature == 0.0:
             nxt = argmax(state.logits)
