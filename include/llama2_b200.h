@@ -213,6 +213,19 @@ int l2b_set_option(l2b_ctx* ctx, const char* key, int64_t value);
 int64_t l2b_tp_export(l2b_ctx* ctx, void* blob, uint64_t cap);
 int     l2b_tp_connect(l2b_ctx* ctx, const void* blobs, uint64_t blob_bytes, int32_t n_ranks);
 
+/* ---- native tokenizer (host code, no device) -----------
+ * tokenizer.bin parse (llama2.ts:441-449), bpe_encode (llama2.ts:305-344: first-match
+ * indexOf semantics, best-score pair merging) and piece lookup (llama2.ts:501-503) for a
+ * node-free host.  l2b_tok_encode returns the token count or L2B_EINVAL (unknown character,
+ * like the reference's throw at :310, or cap too small).                                  */
+typedef struct l2b_tokenizer l2b_tokenizer;
+int l2b_tok_load(const uint8_t* data, uint64_t nbytes, int32_t vocab_size, l2b_tokenizer** out);
+int l2b_tok_encode(const l2b_tokenizer* tok, const char* text_utf8, int32_t* tokens_out, int32_t cap);
+const char* l2b_tok_piece(const l2b_tokenizer* tok, int32_t id);      /* may contain NUL bytes */
+int32_t l2b_tok_piece_len(const l2b_tokenizer* tok, int32_t id);
+float l2b_tok_score(const l2b_tokenizer* tok, int32_t id);
+void l2b_tok_free(l2b_tokenizer* tok);
+
 const char* l2b_last_error(const l2b_ctx* ctx); /* ctx may be NULL: last create error */
 int  l2b_abi_version(void);
 void l2b_destroy(l2b_ctx* ctx);

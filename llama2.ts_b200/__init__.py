@@ -15,4 +15,4 @@ The directory name contains a dot, so import it through the root shim:
 without the built library or without a B200 every compute call raises.
 """
 from . import build, capi, dist, host, synth  # noqa: F401
-from .capi import L2BError, Library, Context  # noqa: F401
+from .capi import L2BError, Library, Context, Tokenizer  # noqa: F401

@@ -5,7 +5,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "l2b.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("l2b.cu", "common.cuh", "decode_kernels.cuh", "batch_gemm.cuh", "mega_kernel.cuh", "sampler.cuh")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("l2b.cu", "common.cuh", "decode_kernels.cuh", "batch_gemm.cuh", "mega_kernel.cuh", "sampler.cuh", "tokenizer.inl")] + [
     os.path.join(HERE, "..", "include", "llama2_b200.h")]
 OUT = os.path.join(HERE, "libllama2_b200.so")
 
@@ -20,7 +20,7 @@ def _deps():
     csrc = os.path.join(HERE, "csrc")
     for f in os.listdir(csrc):
         p = os.path.join(csrc, f)
-        if p not in d and f.endswith((".cu", ".cuh", ".h")):
+        if p not in d and f.endswith((".cu", ".cuh", ".h", ".inl")):
             d.append(p)
     return d
 

@@ -70,6 +70,12 @@ _SIGNATURES = {
     "l2b_set_option": (C.c_int, [_p, C.c_char_p, _i64]),
     "l2b_tp_export": (_i64, [_p, _p, _u64]),
     "l2b_tp_connect": (C.c_int, [_p, C.c_char_p, _u64, _i32]),
+    "l2b_tok_load": (C.c_int, [C.c_char_p, _u64, _i32, C.POINTER(_p)]),
+    "l2b_tok_encode": (C.c_int, [_p, C.c_char_p, _p, _i32]),
+    "l2b_tok_piece": (C.c_void_p, [_p, _i32]),
+    "l2b_tok_piece_len": (_i32, [_p, _i32]),
+    "l2b_tok_score": (_f32, [_p, _i32]),
+    "l2b_tok_free": (None, [_p]),
     "l2b_last_error": (C.c_char_p, [_p]),
     "l2b_abi_version": (C.c_int, []),
     "l2b_destroy": (None, [_p]),
@@ -303,3 +309,42 @@ class Context:
 
     def set_option(self, key, value):
         self._check(self.lib.dll.l2b_set_option(self._h, key.encode(), int(value)))
+
+
+class Tokenizer:
+    """Native tokenizer.bin + bpe_encode (l2b_tok_*); no device needed."""
+
+    def __init__(self, path_or_bytes, vocab_size=32000, lib=None):
+        self.lib = lib or Library.get()
+        data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else open(path_or_bytes, "rb").read()
+        h = _p()
+        rc = self.lib.dll.l2b_tok_load(bytes(data), len(data), vocab_size, C.byref(h))
+        if rc != 0:
+            raise L2BError(rc, "malformed tokenizer.bin")
+        self._h = h
+        self.vocab_size = vocab_size
+
+    def encode(self, text):
+        buf = np.zeros(max(1, len(text.encode("utf-8"))), dtype=np.int32)
+        n = self.lib.dll.l2b_tok_encode(self._h, text.encode("utf-8"), _ptr(buf), buf.size)
+        if n < 0:
+            raise ValueError("Error: character not found in vocab")
+        return buf[:n].copy()
+
+    def piece(self, i):
+        n = self.lib.dll.l2b_tok_piece_len(self._h, int(i))
+        return C.string_at(self.lib.dll.l2b_tok_piece(self._h, int(i)), n).decode("utf-8", errors="replace")
+
+    def score(self, i):
+        return float(self.lib.dll.l2b_tok_score(self._h, int(i)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dll.l2b_tok_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1824,3 +1824,5 @@ L2B_API int l2b_tp_connect(l2b_ctx* c, const void* blobs, uint64_t blob_bytes, i
   drop_graphs(c);
   return L2B_OK;
 }
+
+#include "tokenizer.inl"
