@@ -1564,7 +1564,8 @@ static int enqueue_sampler(l2b_ctx* c, const float* logits, double temperature, 
   sp.cand_i = c->samp_i; sp.sort_i = c->samp_i + c->V;
   sp.next = c->d_dev + 1;
   void* args[] = {&sp};
-  return launch(c, L2B_K_CLS, (const void*)sample_kernel, dim3(1), dim3(kSampThreads), 0, 1, args, c->stream);
+  return launch(c, L2B_K_CLS, (const void*)sample_kernel, dim3(1), dim3(kSampThreads),
+                16 * kSampThreads * sizeof(int), 1, args, c->stream);
 }
 
 L2B_API int l2b_forward_sample(l2b_ctx* c, int32_t token, int32_t pos, double temperature, double topp,
