@@ -299,6 +299,11 @@ class Context:
         joined = b"".join(blobs)
         self._check(self.lib.dll.l2b_tp_connect(self._h, joined, n, len(blobs)))
 
+    def gemv_timeline(self):
+        out = np.zeros((1024, 2, 6), dtype=np.int64)
+        self._check(self.lib.dll.l2b_debug_timeline(self._h, _ptr(out), out.size))
+        return out
+
     def debug_timeline(self):
         out = np.zeros((256, 8), dtype=np.int64)
         self._check(self.lib.dll.l2b_debug_timeline(self._h, _ptr(out), out.size))

@@ -61,6 +61,12 @@ __device__ __forceinline__ void st_relaxed_sys_f32(float* p, float v) {
   asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ long long gtimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---- programmatic dependent launch ------------------------------------------
 __device__ __forceinline__ void griddep_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

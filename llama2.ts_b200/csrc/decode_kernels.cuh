@@ -153,6 +153,11 @@ struct GemvParams {
   int b0, nact, B;
   int evict_first;
   int l2_prefetch;       // bytes of this CTA's weight range pulled into L2 before griddep_wait()
+  int* work;             // != nullptr: row pairs are handed out dynamically from this counter (zero at
+                         // launch): SMs do not stream at equal rates (GPC sizes differ), a static equal
+                         // split leaves the fast ones idle for ~20 % of the kernel
+  long long* dbg;        // optional per-launch timeline (globaltimer ns): [launch][SM-sampled CTA][6]
+  int dbg_slot;
   TpParams tp;           // used by the TP = true instantiations only
 };
 
@@ -244,6 +249,9 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
   __shared__ int s_is_last;
 
   griddep_launch_dependents();
+  const bool dbg_on = p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+  long long* dbg_row = dbg_on ? p.dbg + ((size_t)p.dbg_slot * 2 + (blockIdx.x == 0 ? 0 : 1)) * 6 : nullptr;
+  if (dbg_on) dbg_row[0] = gtimer_ns();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = p.n, n4 = n >> 2;
@@ -252,14 +260,18 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
   const int pair0 = (int)(((long long)npairs * blockIdx.x) / gridDim.x);
   const int pair1 = (int)(((long long)npairs * (blockIdx.x + 1)) / gridDim.x);
   const int tpp = (n4 + 32 * kU - 1) / (32 * kU);  // tiles per pair
-  const int my_first = pair0 + warp;
-  const int my_pairs = my_first < pair1 ? (pair1 - my_first + WARPS - 1) / WARPS : 0;
+  const bool dynamic = p.work != nullptr;
+  const int total_warps = (int)gridDim.x * WARPS;
+  // static: this CTA's contiguous range, warps interleaved; dynamic: first pair by global warp id,
+  // every further pair from the shared counter
+  const int my_first = dynamic ? (int)blockIdx.x * WARPS + warp : pair0 + warp;
+  const int limit = dynamic ? npairs : pair1;
   const float4* W4 = reinterpret_cast<const float4*>(p.W);
   const uint64_t pol = make_l2_policy(p.evict_first != 0);
 
   PairTile cur, nxt;
   int pair = my_first, jt = 0;
-  if (my_pairs > 0) {
+  if (pair < limit) {
     const float4* w0 = W4 + (size_t)(2 * pair) * n4;
     load_pair_tile(cur, w0, w0 + n4, lane, n4, pol);
   }
@@ -268,19 +280,22 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
   // loop's next tiles are L2 hits while the stream behind them ramps up.
   if (p.l2_prefetch > 0 && lane == 0) {
     const size_t cta_bytes = (size_t)(pair1 - pair0) * 2 * n * sizeof(float);
+    const int pf_pair0 = dynamic ? (int)blockIdx.x * WARPS : pair0;
     size_t want = (size_t)p.l2_prefetch < cta_bytes ? (size_t)p.l2_prefetch : cta_bytes;
     const size_t per = ((want / WARPS) + 15) & ~(size_t)15;
     const size_t off = (size_t)warp * per;
     if (per > 0 && off < want) {
       const size_t len = (off + per <= want) ? per : ((want - off) & ~(size_t)15);
       if (len > 0)
-        prefetch_l2_bulk(reinterpret_cast<const unsigned char*>(p.W) + (size_t)pair0 * 2 * n * sizeof(float) + off,
+        prefetch_l2_bulk(reinterpret_cast<const unsigned char*>(p.W) + (size_t)pf_pair0 * 2 * n * sizeof(float) + off,
                          (uint32_t)len);
     }
   }
 
   // ---- everything below may depend on the previous kernel ----
+  if (dbg_on) dbg_row[1] = gtimer_ns();
   griddep_wait();
+  if (dbg_on) dbg_row[2] = gtimer_ns();
   int tp_seq = 0;
   if (TP) tp_seq = ld_act_i32(p.tp.epoch) + 1;
   const bool ll_in = TP && p.tp.ll_in != 0;   // input is an LL replica: spin on its sequence tags
@@ -359,6 +374,7 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
   }
   __syncthreads();
 
+  if (dbg_on) dbg_row[3] = gtimer_ns();
   // lane s of every warp runs the epilogue of sequence b0 + s
   const bool epi_lane = lane < p.nact;
   const int eb = p.b0 + (epi_lane ? lane : 0);
@@ -373,15 +389,25 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
 #pragma unroll
     for (int k = 0; k < KACC; ++k) acc[0][s][k] = acc[1][s][k] = (acc_t)0;
 
-  const int total = my_pairs * tpp;
-  for (int t = 0; t < total; ++t) {
+  bool have = pair < limit;
+  int next_pair = 0;
+  while (have) {
+    if (jt == 0) {  // the pair after this one: the atomic is issued now, its result is only
+                    // consumed when the last tile of the current pair is reached (latency hidden)
+      if (dynamic) {
+        if (lane == 0) next_pair = atomicAdd(p.work, 1) + total_warps;
+      } else {
+        next_pair = pair + WARPS;
+      }
+    }
     // request the next tile before touching the current one
     int npair = pair, njt = jt + 1;
     if (njt == tpp) {
       njt = 0;
-      npair = pair + WARPS;
+      npair = dynamic ? __shfl_sync(0xffffffffu, next_pair, 0) : next_pair;
     }
-    if (t + 1 < total) {
+    const bool more = npair < limit;
+    if (more) {
       const float4* w0 = W4 + (size_t)(2 * npair) * n4;
       load_pair_tile(nxt, w0, w0 + n4, njt * 32 * kU + lane, n4, pol);
     }
@@ -501,8 +527,14 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
     pair = npair;
     jt = njt;
     cur = nxt;
+    have = more;
   }
 
+  if (dbg_on) dbg_row[4] = gtimer_ns();   // warp 0 of this CTA finished its rows
+  if (p.dbg != nullptr) {
+    __syncthreads();
+    if (dbg_on) dbg_row[5] = gtimer_ns(); // all warps of this CTA finished
+  }
   if (EPI == EPI_LOGITS) {
     // device argmax (llama2.ts:364-366) + the state-machine advance of :471-504
     if (lane < NB) {

@@ -49,6 +49,9 @@ struct Options {
   int attn_warp = 2048;  // batched path: one-warp-per-(sequence, head) attention kernel when there are at
                          // least this many (sequence, head) pairs (0 = never); below, the cluster kernel
   int tc_tmem_a = 1;     // N <= 128: weight operand in tensor memory (gemm_3xtf32_tmemA_kernel)
+  int dyn_sched = 0;         // batch-1 GEMV kernels hand out row pairs dynamically (see GemvParams::work);
+                             // measured: CTAs finish together, but 193 vs 199 tok/s -- under PDL the next
+                             // kernel's prefetch already fills the SMs that finish early
   int l2_prefetch = 262144;  // bytes per CTA prefetched into L2 before griddep_wait (0 = off)
   int attn_prefetch = 0;     // attention kernel prefetches the wo weights into L2 (measured net-negative: it
                              // delays the K/V copies in the same queue; kept as an option)
@@ -87,6 +90,9 @@ struct l2b_ctx {
   float* blk_val = nullptr;
   int* blk_idx = nullptr;
   int *d_forced = nullptr, *d_out = nullptr;
+  int* d_work = nullptr;      // dynamic-schedule counters, one per GEMV launch of a step
+  int work_idx = 0, work_cap = 0;
+  bool work_armed = false;    // counters were zeroed for the launches being enqueued right now
   unsigned* d_bar = nullptr;  // grid barrier words of the persistent kernel
   float* samp_f = nullptr;    // device sampler scratch: probs | cand_p | sort_p  (3 x vocab)
   int* samp_i = nullptr;      //                         cand_i | sort_i          (2 x vocab)
@@ -96,6 +102,7 @@ struct l2b_ctx {
   int pf_cap = 0;
   // batched tensor-core path: pre-split activations [256*groups][D or F], partial sums
   float *XhD = nullptr, *XlD = nullptr, *XhF = nullptr, *XlF = nullptr, *P = nullptr;
+  long long* d_dbg2 = nullptr; int gemv_dbg_arm = 0, gemv_dbg_slot = 0;  // GEMV launch timeline (option "gemv_timeline")
   long long* d_dbg = nullptr; // kernel timeline buffer (debug option "gemm_timeline")
   int dbg_arm = 0;
   float* Wt = nullptr;       // tile-major copy of every projection (built at first batched use)
@@ -266,9 +273,14 @@ int pick_nb(const l2b_ctx* c, int B, int n) {
 int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
   if (c->tp_size > 1) {
     gemv_fn fn = pick_kernel_tp(kclass);
-    p.B = 1; p.b0 = 0; p.nact = 1;
+    p.B = 1; p.b0 = 0; p.nact = 1; p.work = nullptr; p.dbg = nullptr;
     void* args[] = {&p};
     return launch(c, kclass, (const void*)fn, dim3(c->num_sms), dim3(512), (size_t)p.n * 8, 1, args, st);
+  }
+  p.dbg = nullptr;
+  if (c->gemv_dbg_arm && c->d_dbg2 && c->gemv_dbg_slot < 1024) {
+    p.dbg = c->d_dbg2;
+    p.dbg_slot = c->gemv_dbg_slot++;
   }
   const int nb = pick_nb(c, B, p.n);
   int threads = c->opt.threads;
@@ -281,6 +293,8 @@ int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
   if (cps * nb * per > 200 * 1024) cps = 1;
   const int grid = c->num_sms * cps;
   p.B = B;
+  p.work = nullptr;
+  if (c->work_armed && nb == 1 && B == 1 && c->work_idx < c->work_cap) p.work = c->d_work + c->work_idx++;
   for (int b0 = 0; b0 < B; b0 += nb) {
     p.b0 = b0;
     p.nact = (B - b0) < nb ? (B - b0) : nb;
@@ -785,6 +799,13 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   base.evict_first = ef;
   base.l2_prefetch = ef ? c->opt.l2_prefetch : 0;  // L2-resident models need no prefetch
 
+  c->work_idx = 0;
+  c->work_armed = false;
+  if (c->opt.dyn_sched && B == 1) {
+    CU(c, cudaMemsetAsync(c->d_work, 0, sizeof(int) * (size_t)c->work_cap, st));
+    c->work_armed = true;
+  }
+
   const int cs = auto_cluster(c, B);
   for (int l = 0; l < c->L; ++l) {
     {  // rmsnorm -> q,k,v -> RoPE -> KV write   (llama2.ts:216-240)
@@ -876,6 +897,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
     p.logits = c->logits;
     p.V = c->V;
     int rc = launch_gemv(c, L2B_K_CLS, p, B, st);
+    c->work_armed = false;
     if (rc) return rc;
   }
   return 0;
@@ -1179,6 +1201,8 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     c->P_floats = (size_t)c->Smax * sB * Mmax;
   }
   TRY(dev_alloc(c, &c->d_bar, 4, true));
+  c->work_cap = 4 * L + 8;
+  TRY(dev_alloc(c, &c->d_work, (size_t)c->work_cap, true));
   TRY(dev_alloc(c, &c->samp_f, 4 * sV, true));
   TRY(dev_alloc(c, &c->samp_i, 2 * sV, true));
   TRY(dev_alloc(c, &c->d_forced, (size_t)max_steps * sB, true));
@@ -1240,7 +1264,7 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
                  c->pf_x, c->pf_xb, c->pf_q, c->Wt};
   for (float* p : fl)
     if (p) cudaFree(p);
-  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->samp_i, (int*)c->samp_f};
+  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->d_work, c->samp_i, (int*)c->samp_f};
   for (int* p : il)
     if (p) cudaFree(p);
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -1722,9 +1746,14 @@ L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer
 }
 
 L2B_API int l2b_debug_timeline(l2b_ctx* c, int64_t* out, uint64_t n) {
-  if (!c || !out || !c->d_dbg) return L2B_EINVAL;
-  if (n > 256 * 8) n = 256 * 8;
+  if (!c || !out) return L2B_EINVAL;
   CU(c, cudaStreamSynchronize(c->stream));
+  if (c->d_dbg2 && n == 1024 * 12) {   // GEMV launch timeline
+    CU(c, cudaMemcpy(out, c->d_dbg2, n * sizeof(long long), cudaMemcpyDeviceToHost));
+    return L2B_OK;
+  }
+  if (!c->d_dbg) return L2B_EINVAL;
+  if (n > 256 * 8) n = 256 * 8;
   CU(c, cudaMemcpy(out, c->d_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost));
   return L2B_OK;
 }
@@ -1763,12 +1792,21 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.evict_first = v < 0 ? -1 : (v != 0);
   } else if (k == "tc_min_batch") {
     o.tc_min_batch = v < 0 ? 0 : v;
+  } else if (k == "dyn_sched") {
+    o.dyn_sched = v != 0;
   } else if (k == "l2_prefetch") {
     o.l2_prefetch = v < 0 ? 0 : v;
   } else if (k == "attn_prefetch") {
     o.attn_prefetch = v != 0;
   } else if (k == "mega") {
     o.mega = v != 0;
+  } else if (k == "gemv_timeline") {
+    if (v && !c->d_dbg2) {
+      if (cudaMalloc((void**)&c->d_dbg2, 1024 * 12 * sizeof(long long)) != cudaSuccess) return fail(c, L2B_ENOMEM, "dbg");
+    }
+    if (c->d_dbg2) cudaMemset(c->d_dbg2, 0, 1024 * 12 * sizeof(long long));
+    c->gemv_dbg_arm = v != 0;
+    c->gemv_dbg_slot = 0;
   } else if (k == "gemm_timeline") {
     if (v && !c->d_dbg) {
       if (cudaMalloc((void**)&c->d_dbg, 256 * 8 * sizeof(long long)) != cudaSuccess) return fail(c, L2B_ENOMEM, "dbg");

@@ -78,6 +78,24 @@ def test_7b_logits_vs_oracle(pkg, oracle, seven_b):
         oracle.set_threads(1)
 
 
+def test_7b_greedy_stream_vs_oracle(pkg, oracle, seven_b):
+    """`-t 0 -i <prompt>` on the full-size model: the first 24 tokens of the device-resident greedy loop
+    are the reference loop's (the oracle costs ~0.4 s per 7B token on the box's host threads)."""
+    hdr, blob, ctx = seven_b
+    ref = oracle.Model(hdr, blob)
+    oracle.set_threads(oracle.max_threads())
+    prompt = np.array([26222, 2501, 263, 931], dtype=np.int32)          # "Once upon a time"
+    try:
+        want, _ = ref.generate(24, prompt, temperature=0.0)
+    finally:
+        oracle.set_threads(1)
+    ctx.reset()
+    forced = np.full(24, -1, dtype=np.int32)
+    forced[:4] = prompt
+    got = ctx.generate_greedy([1], [0], 24, forced)[:, 0]
+    assert np.array_equal(got[:len(want)], want)
+
+
 def test_7b_properties_256_tokens(pkg, oracle, seven_b):
     """Size-independent properties over a 256-token greedy run at full size:
     determinism, device-loop == host-driven loop == graph-less launches, and the first-max
