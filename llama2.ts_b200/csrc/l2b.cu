@@ -25,6 +25,7 @@
 #include "batch_gemm.cuh"
 #include "decode_kernels.cuh"
 #include "mega_kernel.cuh"
+#include "stream_kernel.cuh"
 #include "sampler.cuh"
 
 #define L2B_API extern "C" __attribute__((visibility("default")))
@@ -55,7 +56,10 @@ struct Options {
   int l2_prefetch = 262144;  // bytes per CTA prefetched into L2 before griddep_wait (0 = off)
   int attn_prefetch = 0;     // attention kernel prefetches the wo weights into L2 (measured net-negative: it
                              // delays the K/V copies in the same queue; kept as an option)
-  int mega = 0;          // batch-1: whole step (and greedy loop) as one persistent cooperative kernel
+  int mega = 0;          // batch-1 persistent kernels: 1 = cooperative kernel with grid barriers
+                         // (mega_kernel.cuh), 2 = barrier-free streaming kernel (stream_kernel.cuh)
+  int stream_stages = 0; // mega=2: ring stages per warp (0 = as many as shared memory holds)
+  int stream_chunks = 0; // mega=2: attention time chunks per head (0 = SMs / heads, at most 8)
                          // (experiment, opt-in: measured slower than graph+PDL so far)
 };
 
@@ -94,6 +98,10 @@ struct l2b_ctx {
   int work_idx = 0, work_cap = 0;
   bool work_armed = false;    // counters were zeroed for the launches being enqueued right now
   unsigned* d_bar = nullptr;  // grid barrier words of the persistent kernel
+  uint2* d_ll = nullptr;      // streaming kernel: LL exchange words {value, sequence}; last word: error flag
+  size_t ll_words = 0;
+  unsigned ll_seq = 1;        // next unused sequence number
+  bool ll_used = false;       // a streaming-kernel launch is in flight (finish() reads its error flag)
   float* samp_f = nullptr;    // device sampler scratch: probs | cand_p | sort_p  (3 x vocab)
   int* samp_i = nullptr;      //                         cand_i | sort_i          (2 x vocab)
   // prompt prefill scratch (l2b_prefill): activations of `pf_cap` positions of one sequence
@@ -950,7 +958,111 @@ int launch_mega(l2b_ctx* c, int n_steps, cudaStream_t st) {
 }
 
 bool use_mega(const l2b_ctx* c, int B) {
-  return c->opt.mega && B == 1 && c->Bmax == 1 && c->tp_size == 1 && !c->profiling && c->H <= c->num_sms;
+  return c->opt.mega == 1 && B == 1 && c->Bmax == 1 && c->tp_size == 1 && !c->profiling && c->H <= c->num_sms;
+}
+
+// shared memory plan of the streaming kernel: activation vector (or attention scratch) + rings
+size_t stream_act_bytes(const l2b_ctx* c) {
+  const int nmax = c->D > c->F ? c->D : c->F;
+  size_t act = (size_t)nmax * 8;
+  const size_t attn = ((size_t)((c->steps + 3) & ~3) + (size_t)kSWarps * kAttnMaxHs + 3 * (size_t)kAttnMaxHs) * 4;
+  return act > attn ? act : attn;
+}
+int stream_stages(const l2b_ctx* c, size_t static_smem) {
+  const size_t total = 227 * 1024;
+  const size_t act = stream_act_bytes(c);
+  if (static_smem + act >= total) return 0;
+  int s = (int)((total - static_smem - act) / ((size_t)kSWarps * kSStageFloats * 4));
+  if (s > kSMaxStages) s = kSMaxStages;
+  if (c->opt.stream_stages > 0 && c->opt.stream_stages < s) s = c->opt.stream_stages;
+  return s;
+}
+bool use_stream(const l2b_ctx* c, int B) {
+  if (!(c->opt.mega == 2 && B == 1 && c->tp_size == 1 && !c->profiling)) return false;
+  const int nmax = c->D > c->F ? c->D : c->F;
+  return c->hs <= kAttnMaxHs && c->hs % 4 == 0 && nmax <= kSMaxV4 * kSThreads * 4 && c->D <= kSMaxV4D * kSThreads * 4 && c->D % 4 == 0 && c->F % 4 == 0 &&
+         2 * (c->D / 2 / c->num_sms + 2) <= kSMaxOwn && stream_stages(c, 4096) >= 2;
+}
+
+// Batch-1 streaming kernel: one cooperative launch (co-residency: the CTAs poll each other's
+// outputs) runs n_steps decode steps of sequence 0.
+int launch_stream(l2b_ctx* c, int n_steps, cudaStream_t st) {
+  const size_t D = c->D, F = c->F, H = c->H;
+  const int part_stride = c->hs + 4;
+  // words: q, k, v | error flag | one mailbox per CTA {x, hb, attention partials, argmax candidates}
+  const size_t mbox = (D + F + H * kSMaxChunks * (size_t)part_stride + 2 * (size_t)c->num_sms + 3) & ~(size_t)3;
+  const size_t words = 3 * D + 4 + mbox * (size_t)c->num_sms;
+  if (!c->d_ll) {
+    CU(c, cudaMalloc((void**)&c->d_ll, words * sizeof(uint2)));
+    CU(c, cudaMemsetAsync(c->d_ll, 0, words * sizeof(uint2), st));
+    c->ll_words = words;
+    c->ll_seq = 1;
+  }
+  const unsigned need = (unsigned)n_steps * (unsigned)(c->L + 1) * SK_KINDS;
+  if (c->ll_seq > 0xE0000000u - need) {  // sequence numbers about to wrap: start over on clean words
+    CU(c, cudaMemsetAsync(c->d_ll, 0, c->ll_words * sizeof(uint2), st));
+    c->ll_seq = 1;
+  }
+  StreamParams m;
+  memset(&m, 0, sizeof m);
+  m.D = c->D; m.F = c->F; m.L = c->L; m.H = c->H; m.hs = c->hs; m.V = c->V; m.steps = c->steps;
+  m.tok_emb = c->tok_emb; m.rms_att = c->rms_att; m.wqkv = c->wqkv; m.wo = c->wo; m.rms_ffn = c->rms_ffn;
+  m.w13 = c->w13; m.w2 = c->w2; m.rms_final = c->rms_final; m.fcr = c->fcr; m.fci = c->fci; m.wcls = c->wcls;
+  m.kc = c->kc; m.vc = c->vc;
+  m.kv_layer = (long long)c->H * c->steps * c->hs * c->Bmax;
+  m.logits = c->logits; m.x_out = c->x;
+  m.ctl = c->d_ctl; m.next = c->d_dev + 1; m.forced = c->d_forced; m.out_tokens = c->d_out;
+  uint2* w = c->d_ll;
+  m.q_ll = w; w += D;
+  m.k_ll = w; w += D;
+  m.v_ll = w; w += D;
+  m.err = reinterpret_cast<int*>(w); w += 4;
+  m.x_ll = w; w += D;
+  m.hb_ll = w; w += F;
+  m.part_ll = w; w += H * kSMaxChunks * (size_t)part_stride;
+  m.am_ll = w;
+  m.mbox_stride = (long long)mbox;
+  m.part_stride = part_stride;
+  m.seq0 = c->ll_seq + SK_KINDS;  // layer 0 refers to "layer -1" words it never reads
+  c->ll_seq += need + SK_KINDS;
+  m.n_steps = n_steps;
+  int ef = c->opt.evict_first;
+  if (ef < 0) ef = c->weight_bytes > (size_t)100 * 1024 * 1024;
+  m.evict_first = ef;
+  const void* fn = (const void*)stream_decode_kernel;
+  cudaFuncAttributes fa;
+  CU(c, cudaFuncGetAttributes(&fa, fn));
+  if (!c->smem_set.count(fn)) {
+    CU(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024 - (int)fa.sharedSizeBytes));
+    c->smem_set.insert(fn);
+  }
+  m.stages = stream_stages(c, fa.sharedSizeBytes);
+  if (m.stages < 2) return fail(c, L2B_EINVAL, "streaming kernel: model too large for the shared-memory ring");
+  int gmax = c->num_sms / c->H;
+  if (gmax < 1) gmax = 1;
+  if (gmax > kSMaxChunks) gmax = kSMaxChunks;
+  if (c->opt.stream_chunks > 0 && c->opt.stream_chunks < gmax) gmax = c->opt.stream_chunks;
+  m.gmax = gmax;
+  m.dbg = c->gemv_dbg_arm ? c->d_dbg2 : nullptr;
+  const size_t smem = (size_t)kSWarps * m.stages * kSStageFloats * 4 + stream_act_bytes(c);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(c->num_sms);
+  cfg.blockDim = dim3(kSThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  memset(at, 0, sizeof at);
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  void* args[] = {&m};
+  CU(c, cudaLaunchKernelExC(&cfg, fn, args));
+  c->launch_counter++;
+  c->ll_used = true;
+  return 0;
 }
 
 // Runs `n_steps` decode steps for B sequences, graph-launched when enabled.
@@ -964,6 +1076,14 @@ int run_steps(l2b_ctx* c, int B, int n_steps) {
   if (use_mega(c, B)) {
     CU(c, cudaEventRecord(c->ev0, c->stream));
     int rc = launch_mega(c, n_steps, c->stream);
+    if (rc) return rc;
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    c->last_launches = c->launch_counter - l0;
+    return 0;
+  }
+  if (use_stream(c, B)) {
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    int rc = launch_stream(c, n_steps, c->stream);
     if (rc) return rc;
     CU(c, cudaEventRecord(c->ev1, c->stream));
     c->last_launches = c->launch_counter - l0;
@@ -1015,8 +1135,21 @@ int run_steps(l2b_ctx* c, int B, int n_steps) {
 int finish(l2b_ctx* c) {
   if (c->tp_size > 1)
     CU(c, cudaMemcpyAsync(c->h_err, c->tp_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  const bool ll = c->ll_used && c->tp_size == 1;
+  if (ll) {
+    int* derr = reinterpret_cast<int*>(c->d_ll + 3 * (size_t)c->D);
+    CU(c, cudaMemcpyAsync(c->h_err, derr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(c, cudaStreamSynchronize(c->stream));
   CU(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  if (ll) {
+    c->ll_used = false;
+    if (*c->h_err != 0) {
+      cudaMemsetAsync(c->d_ll, 0, c->ll_words * sizeof(uint2), c->stream);
+      c->ll_seq = 1;
+      return fail(c, L2B_ECOMM, "streaming kernel: activation exchange timed out");
+    }
+  }
   if (c->tp_size > 1 && *c->h_err != 0) {
     cudaMemsetAsync(c->tp_err, 0, sizeof(int), c->stream);
     return fail(c, L2B_ECOMM, "tensor-parallel exchange timed out waiting for a peer rank");
@@ -1264,7 +1397,8 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
                  c->pf_x, c->pf_xb, c->pf_q, c->Wt};
   for (float* p : fl)
     if (p) cudaFree(p);
-  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->d_work, c->samp_i, (int*)c->samp_f};
+  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->d_work, c->samp_i, (int*)c->samp_f,
+               (int*)c->d_ll};
   for (int* p : il)
     if (p) cudaFree(p);
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -1799,7 +1933,11 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
   } else if (k == "attn_prefetch") {
     o.attn_prefetch = v != 0;
   } else if (k == "mega") {
-    o.mega = v != 0;
+    o.mega = v < 0 ? 0 : (v > 2 ? 2 : v);
+  } else if (k == "stream_stages") {
+    o.stream_stages = v < 0 ? 0 : v;
+  } else if (k == "stream_chunks") {
+    o.stream_chunks = v < 0 ? 0 : v;
   } else if (k == "gemv_timeline") {
     if (v && !c->d_dbg2) {
       if (cudaMalloc((void**)&c->d_dbg2, 1024 * 12 * sizeof(long long)) != cudaSuccess) return fail(c, L2B_ENOMEM, "dbg");

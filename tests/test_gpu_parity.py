@@ -98,6 +98,13 @@ def test_greedy_stream_identical(pkg, oracle, arch, seed, std):
         tok = nxt
     assert np.array_equal(np.array(out), want)
     assert len(set(want.tolist())) > 4, "degenerate stream: test would be vacuous"
+    # the experimental streaming kernel runs the whole loop in one launch (forced prompt tokens,
+    # attention split into time chunks once the context is long enough)
+    ctx.reset()
+    ctx.set_option("mega", 2)
+    got2 = ctx.generate_greedy([1], [0], S, forced)[:, 0]
+    ctx.set_option("mega", 0)
+    assert np.array_equal(got2[:n], want), "streaming kernel: token streams differ"
     ctx.close()
 
 
@@ -137,6 +144,11 @@ def test_variants_agree(pkg, oracle):
     mega = run()
     for p in range(len(toks)):
         assert close(mega[p], want[p]), ("mega", p)
+    ctx.set_option("mega", 2)         # opt-in experiment: barrier-free streaming kernel (bulk-copy
+    stream = run()                    # weight rings, LL activation mailboxes), stream_kernel.cuh
+    for p in range(len(toks)):
+        assert close(stream[p], want[p]), ("stream", p)
+    assert np.array_equal(stream[0], want[0]) or np.abs(stream[0] - want[0]).max() < 1e-6
     ctx.set_option("mega", 0)         # default: one kernel per fused op, CUDA graph + PDL
     base = run()
     for opts in ({"graph": 0}, {"pdl": 0}, {"graph": 0, "pdl": 0}, {"threads": 256},

@@ -1,0 +1,168 @@
+// llbench.cu -- floor of the barrier-free activation exchange used by stream_kernel.cuh:
+// every CTA publishes its slice of a D-word vector as {value, seq} words, every CTA then
+// polls the whole vector.  Reports microseconds per exchange for a few variants.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/llbench tools/llbench.cu
+#include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CK(x)                                                                  \
+  do {                                                                         \
+    cudaError_t e = (x);                                                       \
+    if (e != cudaSuccess) {                                                    \
+      printf("%s: %s\n", #x, cudaGetErrorString(e));                           \
+      exit(1);                                                                 \
+    }                                                                          \
+  } while (0)
+
+__device__ __forceinline__ uint4 ldv4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint4 ldrelaxed4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// mode bit 0: push (one mailbox per consumer CTA) instead of pull (one shared copy)
+// mode bit 1: exponential back-off in the poll loop
+// mode bit 2: ld.relaxed.gpu instead of ld.volatile
+// mode bit 3: only warp 0 polls (others wait at the CTA barrier)
+__global__ void __launch_bounds__(512, 1) exch_kernel(uint2* buf, long long half, long long mbox_stride, int D, int iters, int mode, int* err) {
+  const int tid = threadIdx.x, ncta = gridDim.x, cta = blockIdx.x;
+  const int units = D / 2;  // 16-byte units
+  const int u0 = (int)((long long)units * cta / ncta), u1 = (int)((long long)units * (cta + 1) / ncta);
+  const bool push = mode & 1, backoff = mode & 2, relaxed = mode & 4, onewarp = mode & 8;
+  float acc = 0.f;
+  for (int it = 1; it <= iters; ++it) {
+    const uint32_t seq = (uint32_t)it;
+    uint2* cur = buf + (size_t)(it & 1) * half;   // two buffers: a fast CTA never overwrites words still polled
+    // publish my slice (value depends on what I gathered last time: a true dependency chain)
+    if (push) {
+      const int mine = u1 - u0;
+      for (int i = tid; i < mine * ncta; i += 512) {
+        const int c = i / mine, u = u0 + i - c * mine;
+        st4(cur + (size_t)c * mbox_stride + 2 * u, __float_as_uint(acc + u), seq, __float_as_uint(acc), seq);
+      }
+    } else {
+      for (int u = u0 + tid; u < u1; u += 512) st4(cur + 2 * u, __float_as_uint(acc + u), seq, __float_as_uint(acc), seq);
+    }
+    // gather the whole vector
+    const uint2* src = push ? cur + (size_t)cta * mbox_stride : cur;
+    float s = 0.f;
+    const int nthr = onewarp ? 32 : 512;
+    if (tid < nthr) {
+      for (int u = tid; u < units; u += nthr) {
+        const uint4* p = reinterpret_cast<const uint4*>(src) + u;
+        uint4 v = relaxed ? ldrelaxed4(p) : ldv4(p);
+        unsigned spins = 0, ns = 32;
+        while (!(v.y == seq && v.w == seq)) {
+          if (backoff) {
+            __nanosleep(ns);
+            if (ns < 256) ns *= 2;
+          }
+          v = relaxed ? ldrelaxed4(p) : ldv4(p);
+          if (++spins > (1u << 17)) {
+            atomicExch(err, 1);
+            break;
+          }
+        }
+        s += __uint_as_float(v.x) * 1e-9f;
+      }
+    }
+    // CTA-wide reduce, like the rmsnorm in the real kernel
+    __shared__ float red[16];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < 16; ++w) t += red[w];
+    acc = t * 1e-3f;
+  }
+  if (tid == 0 && acc == 12345.f) buf[0].x = 1;
+}
+
+// grid barrier variant for comparison: publish plain, barrier, read plain
+__global__ void __launch_bounds__(512, 1) barrier_kernel(float* vec, int D, int iters) {
+  namespace cg = cooperative_groups;
+  cg::grid_group g = cg::this_grid();
+  const int tid = threadIdx.x, ncta = gridDim.x, cta = blockIdx.x;
+  const int u0 = (int)((long long)D * cta / ncta), u1 = (int)((long long)D * (cta + 1) / ncta);
+  float acc = 0.f;
+  __shared__ float red[16];
+  for (int it = 1; it <= iters; ++it) {
+    float* dst = vec + (size_t)(it & 1) * D;
+    for (int u = u0 + tid; u < u1; u += 512) dst[u] = acc + u;
+    g.sync();
+    float s = 0.f;
+    for (int u = tid; u < D; u += 512) s += __ldcg(dst + u) * 1e-9f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < 16; ++w) t += red[w];
+    acc = t * 1e-3f;
+  }
+  if (tid == 0 && acc == 12345.f) vec[0] = 1;
+}
+
+int main() {
+  int dev = 0, sms = 0;
+  CK(cudaSetDevice(dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int Dmax = 16384;
+  const long long stride = Dmax;
+  uint2* buf;
+  int* err;
+  CK(cudaMalloc(&buf, sizeof(uint2) * (size_t)stride * sms * 2));
+  CK(cudaMalloc(&err, 4));
+  float* vec;
+  CK(cudaMalloc(&vec, sizeof(float) * 2 * Dmax));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int iters = 2000;
+  for (int D : {288, 768, 4096, 11008}) {
+    for (int mode : {0, 2, 4, 6, 1, 3, 8, 10, 9, 11}) {
+      CK(cudaMemset(buf, 0, sizeof(uint2) * (size_t)stride * sms * 2));
+      CK(cudaMemset(err, 0, 4));
+      long long ms = stride, half = stride * sms;
+      int d = D, it = iters, m = mode;
+      void* args[] = {&buf, &half, &ms, &d, &it, &m, &err};
+      CK(cudaEventRecord(e0));
+      CK(cudaLaunchCooperativeKernel((void*)exch_kernel, dim3(sms), dim3(512), args, 0, 0));
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float t;
+      CK(cudaEventElapsedTime(&t, e0, e1));
+      int herr;
+      CK(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
+      printf("D=%5d %s%s%s%s: %.2f us/exchange%s\n", D, (mode & 1) ? "push" : "pull", (mode & 2) ? "+backoff" : "",
+             (mode & 4) ? "+relaxed" : "", (mode & 8) ? "+onewarp" : "", t * 1000.f / iters, herr ? " (TIMEOUT)" : "");
+      fflush(stdout);
+      if (herr) return 1;
+    }
+    {
+      int d = D, it = iters;
+      void* args[] = {&vec, &d, &it};
+      CK(cudaEventRecord(e0));
+      CK(cudaLaunchCooperativeKernel((void*)barrier_kernel, dim3(sms), dim3(512), args, 0, 0));
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float t;
+      CK(cudaEventElapsedTime(&t, e0, e1));
+      printf("D=%5d cooperative-groups grid.sync + plain loads: %.2f us/exchange\n", D, t * 1000.f / iters);
+      fflush(stdout);
+    }
+  }
+  return 0;
+}
