@@ -772,6 +772,21 @@ __device__ __forceinline__ void store_split(float* xh, float* xl, size_t i, floa
   xl[i] = v - h;
 }
 
+// four consecutive elements (index a multiple of 4: contiguous in the xsw_index layout)
+__device__ __forceinline__ void store_split4(float* xh, float* xl, size_t i, float4 v) {
+  float4 h, l;
+  h.x = __uint_as_float(tf32_hi_bits(__float_as_uint(v.x)));
+  h.y = __uint_as_float(tf32_hi_bits(__float_as_uint(v.y)));
+  h.z = __uint_as_float(tf32_hi_bits(__float_as_uint(v.z)));
+  h.w = __uint_as_float(tf32_hi_bits(__float_as_uint(v.w)));
+  l.x = v.x - h.x;
+  l.y = v.y - h.y;
+  l.z = v.z - h.z;
+  l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(xh + i) = h;
+  *reinterpret_cast<float4*>(xl + i) = l;
+}
+
 struct BatVecParams {
   const float* P;        // partial sums [S][B][M] or nullptr
   int S, B, M;
@@ -786,38 +801,116 @@ struct BatVecParams {
 };
 
 // x += sum_s P[s][b][:]  (accum, llama2.ts:168-170)  or  x := emb[token];
-// then rmsnorm (llama2.ts:172-179) -> hi/lo split for the next GEMM.  One CTA per sequence.
-__global__ void __launch_bounds__(256) bat_resid_rms_kernel(const __grid_constant__ BatVecParams p) {
+// then rmsnorm (llama2.ts:172-179) -> hi/lo split for the next GEMM.
+// 65 of these run per step.  CLUSTER = false: one CTA per sequence (large batches, small rows).
+// CLUSTER = true: one cluster of 2/4/8 CTAs per sequence (grid (cluster size, B)), each CTA
+// owns a contiguous slice of the row and the sum of squares is completed through distributed
+// shared memory in fixed rank order -- with one CTA per sequence a batch of 8-32 kept 8-32 SMs
+// busy for ~28 us each time (a quarter of the step).  All loads of a block of 4 float4 per
+// thread are issued before the first is used (L2-only loads: the partial sums were written by
+// the kernel before this one).
+template <bool CLUSTER>
+__device__ __forceinline__ void bat_resid_rms_body(const BatVecParams& p) {
   __shared__ double red[8];
-  griddep_launch_dependents();
-  griddep_wait();
-  const int b = blockIdx.x, D = p.D;
-  float* x = p.x + (size_t)b * D;
+  __shared__ double c_part;
+  constexpr int KQ = 4;
+  const int b = CLUSTER ? blockIdx.y : blockIdx.x, D = p.D, D4 = D >> 2;
+  int q0 = 0, q1 = D4;
+  uint32_t nrank = 1;
+  if (CLUSTER) {
+    nrank = cluster_nctarank();
+    const int per = (D4 + (int)nrank - 1) / (int)nrank;
+    q0 = (int)cluster_ctarank() * per;
+    q1 = (q0 + per < D4) ? q0 + per : D4;
+  }
+  float4* x4 = reinterpret_cast<float4*>(p.x + (size_t)b * D);
+  const float4* emb4 =
+      p.tok_emb != nullptr ? reinterpret_cast<const float4*>(p.tok_emb + (size_t)ld_act_i32(p.tokp + b) * D) : nullptr;
+  const size_t M4 = (size_t)p.M >> 2;
   double ss = 0.0;
-  for (int j = threadIdx.x; j < D; j += 256) {
-    float v;
-    if (p.tok_emb != nullptr) {
-      v = p.tok_emb[(size_t)ld_act_i32(p.tokp + b) * D + j];
-    } else {
-      float add = 0.f;
-      for (int s = 0; s < p.S; ++s) add += ld_act(p.P + ((size_t)s * p.B + b) * p.M + j);
-      v = (float)((double)ld_act(x + j) + (double)add);
+  for (int base = q0; base < q1; base += 256 * KQ) {
+    float4 xv[KQ], acc[KQ];
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int q = base + (int)threadIdx.x + 256 * k;
+      acc[k] = f4_zero();
+      xv[k] = f4_zero();
+      if (q < q1) xv[k] = emb4 != nullptr ? __ldg(emb4 + q) : __ldcg(x4 + q);
     }
-    x[j] = v;
-    ss += (double)v * (double)v;
+    if (emb4 == nullptr) {
+      for (int s = 0; s < p.S; ++s) {
+        const float4* P4 = reinterpret_cast<const float4*>(p.P) + ((size_t)s * p.B + b) * M4;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int q = base + (int)threadIdx.x + 256 * k;
+          if (q < q1) {
+            const float4 t = __ldcg(P4 + q);
+            acc[k].x += t.x;
+            acc[k].y += t.y;
+            acc[k].z += t.z;
+            acc[k].w += t.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int q = base + (int)threadIdx.x + 256 * k;
+      if (q < q1) {
+        float4 v = xv[k];
+        if (emb4 == nullptr) {
+          v.x = (float)((double)xv[k].x + (double)acc[k].x);
+          v.y = (float)((double)xv[k].y + (double)acc[k].y);
+          v.z = (float)((double)xv[k].z + (double)acc[k].z);
+          v.w = (float)((double)xv[k].w + (double)acc[k].w);
+        }
+        x4[q] = v;
+        ss += (double)v.x * (double)v.x + (double)v.y * (double)v.y + (double)v.z * (double)v.z +
+              (double)v.w * (double)v.w;
+      }
+    }
   }
   ss = warp_sum_f64(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
   double tot = 0.0;
+  if (CLUSTER) {
+    if (threadIdx.x == 0) {
+      double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) tot += red[w];
+      for (int w = 0; w < 8; ++w) t += red[w];
+      c_part = t;
+    }
+    cluster_sync_all();
+    for (uint32_t r = 0; r < nrank; ++r) tot += dsmem_ld_f64(dsmem_addr(&c_part, r));
+  } else {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+  }
   tot /= (double)D;
   tot = 1.0 / sqrt(1e-5 + tot);
-  for (int j = threadIdx.x; j < D; j += 256) {
-    const float o = (float)((double)__ldg(p.rms_w + j) * (tot * (double)x[j]));
-    store_split(p.xh, p.xl, xsw_index(b, j, p.npad), o);
+  const float4* w4 = reinterpret_cast<const float4*>(p.rms_w);
+  for (int q = q0 + (int)threadIdx.x; q < q1; q += 256) {
+    const float4 v = x4[q];  // this thread's own stores
+    const float4 w = __ldg(w4 + q);
+    float4 o;
+    o.x = (float)((double)w.x * (tot * (double)v.x));
+    o.y = (float)((double)w.y * (tot * (double)v.y));
+    o.z = (float)((double)w.z * (tot * (double)v.z));
+    o.w = (float)((double)w.w * (tot * (double)v.w));
+    store_split4(p.xh, p.xl, xsw_index(b, 4 * q, p.npad), o);
   }
+  if (CLUSTER) cluster_sync_all();  // nobody exits while a peer may still read its partial sum
+}
+__global__ void __launch_bounds__(256) bat_resid_rms_kernel(const __grid_constant__ BatVecParams p) {
+  griddep_launch_dependents();
+  griddep_wait();
+  bat_resid_rms_body<false>(p);
+}
+__global__ void __launch_bounds__(256) bat_resid_rms_cluster_kernel(const __grid_constant__ BatVecParams p) {
+  griddep_launch_dependents();
+  griddep_wait();
+  bat_resid_rms_body<true>(p);
 }
 
 struct BatQkvParams {
@@ -832,36 +925,49 @@ struct BatQkvParams {
   long long kv_seq_stride;
 };
 
-// RoPE (llama2.ts:224-235) + KV-cache write (:238-240); one thread per row pair.
+// RoPE (llama2.ts:224-235) + KV-cache write (:238-240); one thread per two row pairs (float4).
 __global__ void __launch_bounds__(256) bat_qkv_epi_kernel(const __grid_constant__ BatQkvParams p) {
   griddep_launch_dependents();
   griddep_wait();
   const int b = blockIdx.y;
-  const int pair = blockIdx.x * 256 + threadIdx.x;
+  const int quad = blockIdx.x * 256 + threadIdx.x;
   const int M = 3 * p.D;
-  if (2 * pair >= M) return;
-  const int r = 2 * pair;
-  float s0 = 0.f, s1 = 0.f;
-  for (int s = 0; s < p.S; ++s) {
-    const float2 v = *reinterpret_cast<const float2*>(p.P + ((size_t)s * p.B + b) * M + r);
-    s0 += v.x;
-    s1 += v.y;
-  }
+  const int r = 4 * quad;
+  if (r >= M) return;
+  // latency chain of this short-lived thread: pos -> freq_cis, overlapped with the partial sums
   const int pos = ld_act_i32(p.posp + b);
   const int seg = r / p.D, i = r - seg * p.D;
   const int h = i / p.hs, c = i - h * p.hs;
+  float4 a = f4_zero();
+  for (int s0 = 0; s0 < p.S; s0 += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      v[k] = (s0 + k < p.S) ? __ldcg(reinterpret_cast<const float4*>(p.P + ((size_t)(s0 + k) * p.B + b) * M + r))
+                            : f4_zero();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (s0 + k < p.S) {
+        a.x += v[k].x;
+        a.y += v[k].y;
+        a.z += v[k].z;
+        a.w += v[k].w;
+      }
+    }
+  }
   const size_t row = (size_t)b * p.kv_seq_stride + ((size_t)h * p.steps + pos) * p.hs + c;
   if (seg == 2) {
-    p.vc[row] = s0;
-    p.vc[row + 1] = s1;
+    *reinterpret_cast<float4*>(p.vc + row) = a;
   } else {
-    const double fr = (double)__ldg(p.fcr + (size_t)pos * (p.hs / 2) + c / 2);
-    const double fi = (double)__ldg(p.fci + (size_t)pos * (p.hs / 2) + c / 2);
-    const float o0 = (float)((double)s0 * fr - (double)s1 * fi);
-    const float o1 = (float)((double)s0 * fi + (double)s1 * fr);
+    const float2 fr = __ldg(reinterpret_cast<const float2*>(p.fcr + (size_t)pos * (p.hs / 2) + c / 2));
+    const float2 fi = __ldg(reinterpret_cast<const float2*>(p.fci + (size_t)pos * (p.hs / 2) + c / 2));
+    float4 o;
+    o.x = (float)((double)a.x * (double)fr.x - (double)a.y * (double)fi.x);
+    o.y = (float)((double)a.x * (double)fi.x + (double)a.y * (double)fr.x);
+    o.z = (float)((double)a.z * (double)fr.y - (double)a.w * (double)fi.y);
+    o.w = (float)((double)a.z * (double)fi.y + (double)a.w * (double)fr.y);
     float* dst = seg == 0 ? p.q + (size_t)b * p.D + i : p.kc + row;
-    dst[0] = o0;
-    dst[1] = o1;
+    *reinterpret_cast<float4*>(dst) = o;
   }
 }
 
@@ -873,22 +979,40 @@ struct BatSwigluParams {
   int npad;
 };
 
-// SwiGLU (llama2.ts:284-289) -> pre-split input of the w2 GEMM
+// SwiGLU (llama2.ts:284-289) -> pre-split input of the w2 GEMM; four elements per thread
 __global__ void __launch_bounds__(256) bat_swiglu_kernel(const __grid_constant__ BatSwigluParams p) {
   griddep_launch_dependents();
   griddep_wait();
   const int b = blockIdx.y;
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int i = 4 * (blockIdx.x * 256 + threadIdx.x);
   if (i >= p.F) return;
-  float h1 = 0.f, h3 = 0.f;
-  for (int s = 0; s < p.S; ++s) {
-    const float2 v = *reinterpret_cast<const float2*>(p.P + ((size_t)s * p.B + b) * (2 * (size_t)p.F) + 2 * i);
-    h1 += v.x;
-    h3 += v.y;
+  float4 u = f4_zero(), w = f4_zero();  // {h1[i], h3[i], h1[i+1], h3[i+1]}, {.. i+2, i+3}
+  for (int s0 = 0; s0 < p.S; s0 += 2) {
+    float4 v0[2], v1[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4* src =
+          reinterpret_cast<const float4*>(p.P + ((size_t)(s0 + k) * p.B + b) * (2 * (size_t)p.F) + 2 * i);
+      v0[k] = (s0 + k < p.S) ? __ldcg(src) : f4_zero();
+      v1[k] = (s0 + k < p.S) ? __ldcg(src + 1) : f4_zero();
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (s0 + k < p.S) {
+        u.x += v0[k].x; u.y += v0[k].y; u.z += v0[k].z; u.w += v0[k].w;
+        w.x += v1[k].x; w.y += v1[k].y; w.z += v1[k].z; w.w += v1[k].w;
+      }
+    }
   }
-  const double hv = (double)h1;
-  const float silu = (float)(hv * (1.0 / (1.0 + exp(-hv))));
-  store_split(p.xh, p.xl, xsw_index(b, i, p.npad), (float)((double)silu * (double)h3));
+  // The exponential in fp32 (expf, <= 2 ulp): this path's inputs already carry the 3xTF32
+  // rounding of the GEMM, and 2.8 M fp64 exponentials per launch were what bounded this kernel.
+  auto swiglu = [](float h1, float h3) {
+    const double hv = (double)h1;
+    const float silu = (float)(hv * (1.0 / (1.0 + (double)expf(-h1))));
+    return (float)((double)silu * (double)h3);
+  };
+  const float4 o = make_float4(swiglu(u.x, u.y), swiglu(u.z, u.w), swiglu(w.x, w.y), swiglu(w.z, w.w));
+  store_split4(p.xh, p.xl, xsw_index(b, i, p.npad), o);
 }
 
 struct BatLogitsParams {

@@ -494,7 +494,14 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
     v.tok_emb = emb; v.tokp = tokp; v.x = vw.x; v.rms_w = rms_w;
     v.xh = c->XhD; v.xl = c->XlD; v.npad = c->Bpad; v.D = D;
     void* args[] = {&v};
-    return launch(c, L2B_K_BATCH_EPI, (const void*)bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
+    // cluster size: slices of >= 512 floats, at most ~512 CTAs in total, rows held in registers
+    int C = 8;
+    while (C > 1 && (D / C < 512 || C * B > 512)) C >>= 1;
+    if (B >= 128) C = 1;
+    if (C == 1)
+      return launch(c, L2B_K_BATCH_EPI, (const void*)bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
+    return launch(c, L2B_K_BATCH_EPI, (const void*)bat_resid_rms_cluster_kernel, dim3(C, B), dim3(256), 0, C, args,
+                  st);
   };
 
   rc = resid_rms(nullptr, 0, c->tok_emb, c->rms_att);  // x := embedding; rmsnorm of layer 0
@@ -511,7 +518,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
       q.kc = c->kc + (size_t)l * kv_layer + v.kv_off; q.vc = c->vc + (size_t)l * kv_layer + v.kv_off;
       q.kv_seq_stride = v.kv_stride;
       void* args[] = {&q};
-      rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_qkv_epi_kernel, dim3((3 * D / 2 + 255) / 256, B), dim3(256), 0,
+      rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_qkv_epi_kernel, dim3((3 * D / 4 + 255) / 256, B), dim3(256), 0,
                   1, args, st);
       if (rc) return rc;
     }
@@ -556,7 +563,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
       memset(&w, 0, sizeof w);
       w.P = c->P; w.S = S; w.B = B; w.F = F; w.xh = c->XhF; w.xl = c->XlF; w.npad = c->Bpad;
       void* args[] = {&w};
-      rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_swiglu_kernel, dim3((F + 255) / 256, B), dim3(256), 0, 1, args,
+      rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_swiglu_kernel, dim3((F / 4 + 255) / 256, B), dim3(256), 0, 1, args,
                   st);
       if (rc) return rc;
     }
