@@ -412,6 +412,9 @@ def main():
               K.K_GEMM_CLS: 4 * V * D + act * (D + V), K.K_BATCH_EPI: 0}
     kflops = {K.K_GEMM_QKV: 2.0 * 3 * D * D * B, K.K_GEMM_WO: 2.0 * D * D * B,
               K.K_GEMM_W13: 2.0 * 2 * F * D * B, K.K_GEMM_W2: 2.0 * D * F * B, K.K_GEMM_CLS: 2.0 * V * D * B}
+    fused_attn = B == 1 and kn[K.K_ATTN] == 0 and kn[K.K_QKV] > 0   # q/k/v rows + attention in one kernel
+    if fused_attn:
+        kbytes[K.K_QKV] += kv_b
     if tp:   # every rank streams 1/world of each weight matrix
         kbytes = {k: v / world for k, v in kbytes.items()}
     peak, peak_src = peaks()
@@ -427,7 +430,7 @@ def main():
                 d["gbs"] = round(kbytes[k] / (avg_ms * 1e-3) / 1e9, 1)
             if k in kflops:
                 d["tflops_3xtf32"] = round(3 * kflops[k] / (avg_ms * 1e-3) / 1e12, 1)
-            per_kernel[K.KERNEL_NAMES[k]] = d
+            per_kernel[K.KERNEL_NAMES[k] + ("_attention" if (fused_attn and k == K.K_QKV) else "")] = d
     dom = max((k for k in range(K.K_COUNT) if k != K.K_BATCH_EPI), key=lambda k: kms[k])
     dom_ms = kms[dom] / kn[dom]
     hbm_rate = kbytes[dom] / (dom_ms * 1e-3) / 1e9

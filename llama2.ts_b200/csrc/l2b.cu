@@ -26,6 +26,7 @@
 #include "decode_kernels.cuh"
 #include "mega_kernel.cuh"
 #include "stream_kernel.cuh"
+#include "fused_qkv_attn.cuh"
 #include "sampler.cuh"
 
 #define L2B_API extern "C" __attribute__((visibility("default")))
@@ -58,6 +59,7 @@ struct Options {
                              // delays the K/V copies in the same queue; kept as an option)
   int mega = 0;          // batch-1 persistent kernels: 1 = cooperative kernel with grid barriers
                          // (mega_kernel.cuh), 2 = barrier-free streaming kernel (stream_kernel.cuh)
+  int fuse_qkv_attn = 1; // batch-1: q/k/v rows and the attention of a layer in one cluster kernel
   int stream_stages = 0; // mega=2: ring stages per warp (0 = as many as shared memory holds)
   int stream_chunks = 0; // mega=2: attention time chunks per head (0 = SMs / heads, at most 8)
                          // (experiment, opt-in: measured slower than graph+PDL so far)
@@ -822,7 +824,37 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   }
 
   const int cs = auto_cluster(c, B);
+  // fused q/k/v + attention: one cluster per head
+  int fcs = 8;
+  while (fcs > 1 && (c->H * fcs > c->num_sms || 3 * hs / 2 < fcs)) fcs >>= 1;
+  const bool fuse = c->opt.fuse_qkv_attn && B == 1 && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64;
   for (int l = 0; l < c->L; ++l) {
+    if (fuse) {  // rmsnorm -> q,k,v -> RoPE -> KV write -> attention   (llama2.ts:216-267)
+      QkvAttnParams f;
+      memset(&f, 0, sizeof f);
+      f.W = c->wqkv + (size_t)l * 3 * D * D;
+      f.D = D; f.H = H; f.hs = hs; f.steps = c->steps;
+      f.vin = c->x;
+      f.rms_w = c->rms_att + (size_t)l * D;
+      f.tok_emb = (l == 0) ? c->tok_emb : nullptr;
+      f.tokp = c->d_ctl + CTL_HDR;
+      f.posp = c->d_ctl + CTL_HDR + B;
+      f.x = c->x;
+      f.q = c->q;
+      f.kc = c->kc + (size_t)l * kv_layer;
+      f.vc = c->vc + (size_t)l * kv_layer;
+      f.fcr = c->fcr; f.fci = c->fci;
+      f.xb = c->xb;
+      f.tileT = kAttnStageBytes / (hs * 4);
+      f.sc_cap = ((c->steps + fcs - 1) / fcs + 3) & ~3;
+      f.evict_first = ef;
+      f.l2_prefetch = ef ? c->opt.l2_prefetch : 0;
+      const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
+      void* args[] = {&f};
+      int rc = launch(c, L2B_K_QKV, (const void*)qkv_attn_kernel, dim3(fcs, H, 1), dim3(kFThreads), smem, fcs, args,
+                      st);
+      if (rc) return rc;
+    } else {
     {  // rmsnorm -> q,k,v -> RoPE -> KV write   (llama2.ts:216-240)
       GemvParams p = base;
       p.W = c->wqkv + (size_t)l * 3 * D * D;
@@ -866,6 +898,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       int rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B),
                       dim3(kAttnThreads), smem, cs, args, st);
       if (rc) return rc;
+    }
     }
     {  // wo matvec + residual (llama2.ts:270-273)
       GemvParams p = base;
@@ -1939,6 +1972,8 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.l2_prefetch = v < 0 ? 0 : v;
   } else if (k == "attn_prefetch") {
     o.attn_prefetch = v != 0;
+  } else if (k == "fuse_qkv_attn") {
+    o.fuse_qkv_attn = v != 0;
   } else if (k == "mega") {
     o.mega = v < 0 ? 0 : (v > 2 ? 2 : v);
   } else if (k == "stream_stages") {

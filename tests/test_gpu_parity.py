@@ -164,6 +164,20 @@ def test_variants_agree(pkg, oracle):
         for k in opts:
             ctx.set_option(k, {"graph": 1, "pdl": 1, "threads": 512, "ctas_per_sm": 1,
                                "attn_cluster": 0, "evict_first": -1, "dyn_sched": 0, "l2_prefetch": 262144}[k])
+    # separate q/k/v and attention kernels (the default fuses them per head in one cluster kernel):
+    # same GEMV arithmetic, attention sums in a different order -> tolerance; pos 0 is exact
+    ctx.set_option("fuse_qkv_attn", 0)
+    split = run()
+    for p in range(len(toks)):
+        assert close(split[p], want[p]), ("unfused", p)
+    assert np.array_equal(split[0], base[0])
+    for cs in (1, 2, 4):
+        ctx.set_option("attn_cluster", cs)
+        got = run()
+        for p in range(len(toks)):
+            assert close(got[p], want[p]), ("unfused cluster", cs, p)
+    ctx.set_option("attn_cluster", 0)
+    ctx.set_option("fuse_qkv_attn", 1)
     ctx.set_option("f64", 0)
     got = run()
     for p in range(len(toks)):
