@@ -108,6 +108,29 @@ def test_greedy_stream_identical(pkg, oracle, arch, seed, std):
     ctx.close()
 
 
+@pytest.mark.parametrize("fuse,cluster", [(1, 0), (0, 0), (0, 2)])
+def test_long_context_attention_ring(pkg, oracle, fuse, cluster):
+    """One head of 128 over 1024 positions: every CTA of the attention cluster streams several
+    K and V tiles per pass, so the bulk-copy ring wraps (stages are re-armed behind the empty
+    barriers) -- in the fused q/k/v+attention kernel and in the stand-alone attention kernel."""
+    hdr = pkg.synth.header((128, 344, 2, 1, 512, 1024, True))
+    _, blob = pkg.synth.checkpoint_blob(hdr, seed=41, std=0.06)
+    ref = oracle.Model(hdr, blob)
+    S, V = hdr[6], abs(hdr[5])
+    toks = np.concatenate([[1], pkg.synth.teacher_tokens(S - 1, V, 41)])
+    with pkg.Context(hdr, max_steps=S) as ctx:
+        pkg.synth.upload_blob(ctx, hdr, blob)
+        ctx.set_option("fuse_qkv_attn", fuse)
+        ctx.set_option("attn_cluster", cluster)
+        worst = 0.0
+        for pos in range(S):
+            got = ctx.forward(int(toks[pos]), pos)
+            want = ref.forward(int(toks[pos]), pos)
+            worst = max(worst, float(np.abs(got - want).max()))
+            assert close(got, want), (pos, worst)
+        print("long context (fuse=%d, cluster=%d): max |dlogit| %.3g" % (fuse, cluster, worst))
+
+
 def test_argmax_first_max_wins(pkg, oracle):
     """Duplicate classifier rows give exactly equal logits: argmax must return the lowest
     index (llama2.ts:364-366), on every CTA/warp boundary."""

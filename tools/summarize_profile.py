@@ -12,7 +12,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
-NAMES = {"<1, 0,": "qkv_rope_kvwrite", "<1, 2,": "w13_swiglu", "<1, 3,": "cls_argmax", "attn_decode": "attention"}
+NAMES = {"qkv_attn": "qkv_rope_kvwrite_attention", "<1, 0,": "qkv_rope_kvwrite", "<1, 2,": "w13_swiglu", "<1, 3,": "cls_argmax", "attn_decode": "attention"}
 
 
 def kname(k, grid_rows=None):
