@@ -41,6 +41,10 @@ struct QkvAttnParams {
   int tileT, sc_cap;
   int evict_first;
   int l2_prefetch;
+  // the attention part leaves HBM idle: meanwhile pull the NEXT kernel's weights (wo of this
+  // layer) into L2.  The K/V copies of this CTA were issued long before, nothing queues behind.
+  const unsigned char* pf_ptr;
+  long long pf_bytes;
 };
 
 __device__ __forceinline__ void dsmem_st_f32(uint32_t addr, float v) {
@@ -253,6 +257,17 @@ __global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_con
       pi = npi;
       jt = njt;
       cur = nxt;
+    }
+  }
+  if (p.pf_bytes > 0 && lane == 0) {
+    const long long n_warp = (long long)gridDim.x * gridDim.y * kFWarps;
+    const long long me = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * kFWarps + warp;
+    const long long per = ((p.pf_bytes / n_warp) + 15) & ~15LL;
+    long long off = me * per;
+    const long long end = off + per < p.pf_bytes ? off + per : p.pf_bytes;
+    for (; off + 16 <= end; off += 32768) {
+      const long long len = (end - off < 32768 ? end - off : 32768) & ~15LL;
+      if (len > 0) prefetch_l2_bulk(p.pf_ptr + off, (uint32_t)len);
     }
   }
   cluster_sync_all();  // q, k, v of this head are in every CTA's shared memory

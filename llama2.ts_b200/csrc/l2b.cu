@@ -60,6 +60,8 @@ struct Options {
   int mega = 0;          // batch-1 persistent kernels: 1 = cooperative kernel with grid barriers
                          // (mega_kernel.cuh), 2 = barrier-free streaming kernel (stream_kernel.cuh)
   int fuse_qkv_attn = 1; // batch-1: q/k/v rows and the attention of a layer in one cluster kernel
+  int fuse_prefetch = 0; // ... optionally pulling this percentage of wo into L2 while its attention part runs
+                         // (measured net-negative: wo 20.0 -> 16.6 us but the fused kernel 46.0 -> 50.6 us)
   int stream_stages = 0; // mega=2: ring stages per warp (0 = as many as shared memory holds)
   int stream_chunks = 0; // mega=2: attention time chunks per head (0 = SMs / heads, at most 8)
                          // (experiment, opt-in: measured slower than graph+PDL so far)
@@ -849,6 +851,10 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       f.sc_cap = ((c->steps + fcs - 1) / fcs + 3) & ~3;
       f.evict_first = ef;
       f.l2_prefetch = ef ? c->opt.l2_prefetch : 0;
+      if (ef && c->opt.fuse_prefetch) {
+        f.pf_ptr = reinterpret_cast<const unsigned char*>(c->wo + (size_t)l * D * D);
+        f.pf_bytes = (long long)D * D * sizeof(float) * c->opt.fuse_prefetch / 100;
+      }
       const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
       void* args[] = {&f};
       int rc = launch(c, L2B_K_QKV, (const void*)qkv_attn_kernel, dim3(fcs, H, 1), dim3(kFThreads), smem, fcs, args,
@@ -1972,6 +1978,8 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.l2_prefetch = v < 0 ? 0 : v;
   } else if (k == "attn_prefetch") {
     o.attn_prefetch = v != 0;
+  } else if (k == "fuse_prefetch") {
+    o.fuse_prefetch = v < 0 ? 0 : (v > 100 ? 100 : v);
   } else if (k == "fuse_qkv_attn") {
     o.fuse_qkv_attn = v != 0;
   } else if (k == "mega") {
