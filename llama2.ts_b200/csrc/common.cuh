@@ -27,17 +27,18 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p, uint64_t pol) {
   return r;
 }
 
-// Activations written by the previous kernel: plain coherent loads (never .nc:
-// with programmatic dependent launch the producer may still be running when
-// this kernel starts; the data is only read after griddep_wait()).
+// Activations written by the previous kernel: loads that are coherent at GPU scope (served
+// by L2; never .nc, never a possibly stale L1 line): with programmatic dependent launch the
+// producer may still be running when this kernel starts, and with the software hand-over
+// below it has not formally completed when the data is read.
 __device__ __forceinline__ float ld_act(const float* p) {
   float r;
-  asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
   return r;
 }
 __device__ __forceinline__ float4 ld_act4(const float4* p) {
   float4 r;
-  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p)
                : "memory");
@@ -45,7 +46,7 @@ __device__ __forceinline__ float4 ld_act4(const float4* p) {
 }
 __device__ __forceinline__ int ld_act_i32(const int* p) {
   int r;
-  asm volatile("ld.global.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
   return r;
 }
 // system-scope acquire/release used by the tensor-parallel exchange flags
@@ -73,6 +74,31 @@ __device__ __forceinline__ void griddep_launch_dependents() {
 }
 __device__ __forceinline__ void griddep_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ---- software hand-over between consecutive kernels of a step ------------------
+// Measured on B200 (tools/gemv_timeline.py): after the last CTA of a kernel exits, its
+// programmatic dependent only returns from griddepcontrol.wait 3.5-4.5 us later (grid
+// completion + flush + release), 129 times per Llama-2-7B token.  A kernel of the batch-1
+// decode chain therefore never executes griddepcontrol.wait; it was launched early anyway
+// (programmatic stream serialization) and waits here until every CTA of its predecessor has
+// bumped that predecessor's counter -- the arrive/poll half of a grid barrier (~1.3 us).
+// Counters are zeroed by a memset node at the start of the step's graph.
+__device__ __forceinline__ void soft_signal(int* ctr) {
+  __syncthreads();  // every thread's results are written ...
+  if (threadIdx.x == 0) {
+    __threadfence();  // ... and visible at GPU scope before the arrival is
+    atomicAdd(ctr, 1);
+  }
+}
+__device__ __forceinline__ void soft_wait(const int* ctr, int target) {
+  if (threadIdx.x == 0) {
+    int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
 }
 
 // ---- warp reductions --------------------------------------------------------

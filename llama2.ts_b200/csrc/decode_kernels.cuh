@@ -158,6 +158,11 @@ struct GemvParams {
                          // split leaves the fast ones idle for ~20 % of the kernel
   long long* dbg;        // optional per-launch timeline (globaltimer ns): [launch][SM-sampled CTA][6]
   int dbg_slot;
+  // software hand-over (common.cuh): wait for `sync_target` arrivals on sync_wait instead of
+  // griddepcontrol.wait (nullptr: griddepcontrol.wait), arrive on sync_done at the end
+  const int* sync_wait;
+  int sync_target;
+  int* sync_done;
   TpParams tp;           // used by the TP = true instantiations only
 };
 
@@ -294,7 +299,11 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
 
   // ---- everything below may depend on the previous kernel ----
   if (dbg_on) dbg_row[1] = gtimer_ns();
-  griddep_wait();
+  if (!TP && p.sync_wait != nullptr) {
+    soft_wait(p.sync_wait, p.sync_target);
+  } else {
+    griddep_wait();
+  }
   if (dbg_on) dbg_row[2] = gtimer_ns();
   int tp_seq = 0;
   if (TP) tp_seq = ld_act_i32(p.tp.epoch) + 1;
@@ -531,6 +540,7 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
   }
 
   if (dbg_on) dbg_row[4] = gtimer_ns();   // warp 0 of this CTA finished its rows
+  if (!TP && p.sync_done != nullptr) soft_signal(p.sync_done);
   if (p.dbg != nullptr) {
     __syncthreads();
     if (dbg_on) dbg_row[5] = gtimer_ns(); // all warps of this CTA finished

@@ -45,6 +45,10 @@ struct QkvAttnParams {
   // layer) into L2.  The K/V copies of this CTA were issued long before, nothing queues behind.
   const unsigned char* pf_ptr;
   long long pf_bytes;
+  // software hand-over (common.cuh)
+  const int* sync_wait;
+  int sync_target;
+  int* sync_done;
 };
 
 __device__ __forceinline__ void dsmem_st_f32(uint32_t addr, float v) {
@@ -114,7 +118,11 @@ __global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_con
   __syncthreads();  // mbarrier init visible to the CTA
 
   // ---- everything below may depend on the previous kernel ----
-  griddep_wait();
+  if (p.sync_wait != nullptr) {
+    soft_wait(p.sync_wait, p.sync_target);
+  } else {
+    griddep_wait();
+  }
   const int pos = ld_act_i32(p.posp);
   const int n_t = pos + 1;
 
@@ -440,6 +448,7 @@ __global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_con
     p.xb[(size_t)h * hs + tid] = s;
   }
   cluster_sync_all();  // keep every CTA's shared memory alive until rank 0 has read it
+  if (p.sync_done != nullptr) soft_signal(p.sync_done);
 }
 
 }  // namespace l2b

@@ -60,6 +60,9 @@ struct Options {
   int mega = 0;          // batch-1 persistent kernels: 1 = cooperative kernel with grid barriers
                          // (mega_kernel.cuh), 2 = barrier-free streaming kernel (stream_kernel.cuh)
   int fuse_qkv_attn = 1; // batch-1: q/k/v rows and the attention of a layer in one cluster kernel
+  int soft_sync = 0;     // batch-1: consecutive kernels hand over through arrival counters instead of
+                         // griddepcontrol.wait.  Measured slower (7B 216.5 vs 220.0 tok/s, stories15M 138 vs
+                         // 116 us/token): the gap after a kernel is its slowest CTA, not the release latency
   int fuse_prefetch = 0; // ... optionally pulling this percentage of wo into L2 while its attention part runs
                          // (measured net-negative: wo 20.0 -> 16.6 us but the fused kernel 46.0 -> 50.6 us)
   int stream_stages = 0; // mega=2: ring stages per warp (0 = as many as shared memory holds)
@@ -99,6 +102,8 @@ struct l2b_ctx {
   int* blk_idx = nullptr;
   int *d_forced = nullptr, *d_out = nullptr;
   int* d_work = nullptr;      // dynamic-schedule counters, one per GEMV launch of a step
+  int* d_sync = nullptr;      // software hand-over counters, one per kernel of a batch-1 step
+  int sync_idx = -1, sync_prev_grid = 0; // chain state while a batch-1 step is being enqueued (-1: off)
   int work_idx = 0, work_cap = 0;
   bool work_armed = false;    // counters were zeroed for the launches being enqueued right now
   unsigned* d_bar = nullptr;  // grid barrier words of the persistent kernel
@@ -305,6 +310,17 @@ int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
   if (cps * nb * per > 200 * 1024) cps = 1;
   const int grid = c->num_sms * cps;
   p.B = B;
+  p.sync_wait = nullptr;
+  p.sync_done = nullptr;
+  if (c->sync_idx >= 0 && nb == 1 && B == 1 && c->sync_idx < c->work_cap) {
+    if (c->sync_idx > 0) {
+      p.sync_wait = c->d_sync + c->sync_idx - 1;
+      p.sync_target = c->sync_prev_grid;
+    }
+    if (kclass != L2B_K_CLS) p.sync_done = c->d_sync + c->sync_idx;
+    c->sync_idx++;
+    c->sync_prev_grid = grid;
+  }
   p.work = nullptr;
   if (c->work_armed && nb == 1 && B == 1 && c->work_idx < c->work_cap) p.work = c->d_work + c->work_idx++;
   for (int b0 = 0; b0 < B; b0 += nb) {
@@ -786,6 +802,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
 
 // One decode step for B sequences: tokens/positions are read from d_ctl.
 int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
+  c->sync_idx = -1;
   if (c->tp_size > 1) return enqueue_step_tp(c, st);
   if (c->opt.tc_min_batch > 0 && B >= c->opt.tc_min_batch && c->P != nullptr) {
     BatchView v = {c->x, c->xb, c->q, c->d_ctl, 0, (long long)c->H * c->steps * c->hs, 0};
@@ -830,6 +847,12 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   int fcs = 8;
   while (fcs > 1 && (c->H * fcs > c->num_sms || 3 * hs / 2 < fcs)) fcs >>= 1;
   const bool fuse = c->opt.fuse_qkv_attn && B == 1 && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64;
+  c->sync_idx = -1;
+  if (fuse && c->opt.soft_sync && 4 * c->L + 1 <= c->work_cap) {
+    CU(c, cudaMemsetAsync(c->d_sync, 0, sizeof(int) * (size_t)c->work_cap, st));
+    c->sync_idx = 0;
+    c->sync_prev_grid = 0;
+  }
   for (int l = 0; l < c->L; ++l) {
     if (fuse) {  // rmsnorm -> q,k,v -> RoPE -> KV write -> attention   (llama2.ts:216-267)
       QkvAttnParams f;
@@ -854,6 +877,15 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       if (ef && c->opt.fuse_prefetch) {
         f.pf_ptr = reinterpret_cast<const unsigned char*>(c->wo + (size_t)l * D * D);
         f.pf_bytes = (long long)D * D * sizeof(float) * c->opt.fuse_prefetch / 100;
+      }
+      if (c->sync_idx >= 0) {
+        if (c->sync_idx > 0) {
+          f.sync_wait = c->d_sync + c->sync_idx - 1;
+          f.sync_target = c->sync_prev_grid;
+        }
+        f.sync_done = c->d_sync + c->sync_idx;
+        c->sync_idx++;
+        c->sync_prev_grid = fcs * H;
       }
       const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
       void* args[] = {&f};
@@ -952,6 +984,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
     p.V = c->V;
     int rc = launch_gemv(c, L2B_K_CLS, p, B, st);
     c->work_armed = false;
+    c->sync_idx = -1;
     if (rc) return rc;
   }
   return 0;
@@ -1382,6 +1415,7 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
   TRY(dev_alloc(c, &c->d_bar, 4, true));
   c->work_cap = 4 * L + 8;
   TRY(dev_alloc(c, &c->d_work, (size_t)c->work_cap, true));
+  TRY(dev_alloc(c, &c->d_sync, (size_t)c->work_cap, true));
   TRY(dev_alloc(c, &c->samp_f, 4 * sV, true));
   TRY(dev_alloc(c, &c->samp_i, 2 * sV, true));
   TRY(dev_alloc(c, &c->d_forced, (size_t)max_steps * sB, true));
@@ -1443,7 +1477,7 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
                  c->pf_x, c->pf_xb, c->pf_q, c->Wt};
   for (float* p : fl)
     if (p) cudaFree(p);
-  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->d_work, c->samp_i, (int*)c->samp_f,
+  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->d_work, c->d_sync, c->samp_i, (int*)c->samp_f,
                (int*)c->d_ll};
   for (int* p : il)
     if (p) cudaFree(p);
@@ -1978,6 +2012,8 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.l2_prefetch = v < 0 ? 0 : v;
   } else if (k == "attn_prefetch") {
     o.attn_prefetch = v != 0;
+  } else if (k == "soft_sync") {
+    o.soft_sync = v != 0;
   } else if (k == "fuse_prefetch") {
     o.fuse_prefetch = v < 0 ? 0 : (v > 100 ? 100 : v);
   } else if (k == "fuse_qkv_attn") {
