@@ -49,13 +49,26 @@ struct QkvAttnParams {
   const int* sync_wait;
   int sync_target;
   int* sync_done;
+  // tensor parallel (TP = true instantiation): this rank owns H of the model's heads; wqkv holds
+  // its rows as three segments of seg_rows; x arrives as an LL replica tagged with sequence
+  // epoch + 1 + tp_wait_idx (layer 0: the embedding row); the output slice goes to every peer's
+  // xb replica as LL words tagged epoch + 1 + tp_out_idx
+  int seg_rows;            // rows per q/k/v segment of W (== D when not sharded)
+  int tp_size;
+  int tp_ll_in;
+  const int* tp_epoch;
+  int tp_wait_idx, tp_out_idx;
+  int xb_off;              // column of head 0 of this rank in the gathered xb
+  int* tp_err;
+  float* peer_xb[kMaxTp];
 };
 
 __device__ __forceinline__ void dsmem_st_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_constant__ QkvAttnParams p) {
+template <bool TP>
+__device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
   typedef XVec<true> XV;
   extern __shared__ __align__(128) unsigned char f_smem[];
   // dynamic: activation vector (doubles) | K/V ring | scores
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_con
   const int tpp = (n4 + 32 * kU - 1) / (32 * kU);
   auto first_row = [&](int pi) {            // global row of pair pi in wqkv
     const int seg = pi / half;
-    return seg * D + h * hs + 2 * (pi - seg * half);
+    return seg * p.seg_rows + h * hs + 2 * (pi - seg * half);
   };
   PairTile cur, nxt;
   int pi = pi0 + warp;
@@ -125,6 +138,8 @@ __global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_con
   }
   const int pos = ld_act_i32(p.posp);
   const int n_t = pos + 1;
+  int tp_seq = 0;
+  if (TP) tp_seq = ld_act_i32(p.tp_epoch) + 1;
 
   // attention chunk of this CTA; rows before `pos` come from the cache (earlier steps), the
   // newest row from shared memory
@@ -160,12 +175,21 @@ __global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_con
     const float* src = p.tok_emb != nullptr ? p.tok_emb + (size_t)ld_act_i32(p.tokp) * D : p.vin;
     const float4* src4 = reinterpret_cast<const float4*>(src);
     const bool write_x = p.tok_emb != nullptr && rank == 0 && h == 0;
+    const bool ll_in = TP && p.tp_ll_in != 0;
     double ss = 0.0;
     for (int j = tid; j < n4; j += kFThreads) {
-      const float4 v = ld_act4(src4 + j);
+      const float4 v = ll_in ? ll_load4(p.vin, j, true, tp_seq + p.tp_wait_idx, p.tp_err) : ld_act4(src4 + j);
       ss += (double)v.x * (double)v.x + (double)v.y * (double)v.y + (double)v.z * (double)v.z +
             (double)v.w * (double)v.w;
-      if (write_x) reinterpret_cast<float4*>(p.x)[j] = v;
+      if (write_x) {
+        if (TP) {  // x is an LL replica on every rank
+          uint4* xl = reinterpret_cast<uint4*>(p.x) + 2 * (size_t)j;
+          xl[0] = make_uint4(__float_as_uint(v.x), 0u, __float_as_uint(v.y), 0u);
+          xl[1] = make_uint4(__float_as_uint(v.z), 0u, __float_as_uint(v.w), 0u);
+        } else {
+          reinterpret_cast<float4*>(p.x)[j] = v;
+        }
+      }
     }
     ss = warp_sum_f64(ss);
     if (lane == 0) red_scratch[warp] = ss;
@@ -177,7 +201,7 @@ __global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_con
     tot = 1.0 / sqrt(1e-5 + tot);
     const float4* rw4 = reinterpret_cast<const float4*>(p.rms_w);
     for (int j = tid; j < n4; j += kFThreads) {
-      const float4 v = ld_act4(src4 + j);
+      const float4 v = ll_in ? ll_load4(p.vin, j, false, 0, nullptr) : ld_act4(src4 + j);
       const float4 w = __ldg(rw4 + j);
       float4 o;
       o.x = (float)((double)w.x * (tot * (double)v.x));
@@ -445,10 +469,23 @@ __global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_con
   if (rank == 0 && tid < hs) {
     float s = 0.f;
     for (uint32_t r = 0; r < CS; ++r) s += dsmem_ld_f32(dsmem_addr(&c_out[tid], r));
-    p.xb[(size_t)h * hs + tid] = s;
+    if (!TP) {
+      p.xb[(size_t)h * hs + tid] = s;
+    } else {
+      const size_t o = (size_t)p.xb_off + (size_t)h * hs + tid;
+      const uint32_t sq = (uint32_t)(tp_seq + p.tp_out_idx);
+      for (int r = 0; r < p.tp_size; ++r)
+        st_sys_u2(reinterpret_cast<uint2*>(p.peer_xb[r]) + o, __float_as_uint(s), sq);
+    }
   }
   cluster_sync_all();  // keep every CTA's shared memory alive until rank 0 has read it
   if (p.sync_done != nullptr) soft_signal(p.sync_done);
+}
+__global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_constant__ QkvAttnParams p) {
+  qkv_attn_body<false>(p);
+}
+__global__ void __launch_bounds__(kFThreads, 1) qkv_attn_tp_kernel(const __grid_constant__ QkvAttnParams p) {
+  qkv_attn_body<true>(p);
 }
 
 }  // namespace l2b

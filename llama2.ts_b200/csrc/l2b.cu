@@ -63,6 +63,7 @@ struct Options {
   int soft_sync = 0;     // batch-1: consecutive kernels hand over through arrival counters instead of
                          // griddepcontrol.wait.  Measured slower (7B 216.5 vs 220.0 tok/s, stories15M 138 vs
                          // 116 us/token): the gap after a kernel is its slowest CTA, not the release latency
+  int fuse_cluster = 0;  // CTAs per head of the fused kernel (0 = largest of 8/4/2/1 that fits the SMs)
   int fuse_prefetch = 0; // ... optionally pulling this percentage of wo into L2 while its attention part runs
                          // (measured net-negative: wo 20.0 -> 16.6 us but the fused kernel 46.0 -> 50.6 us)
   int stream_stages = 0; // mega=2: ring stages per warp (0 = as many as shared memory holds)
@@ -679,8 +680,51 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
     cs = 8;
     while (cs > 1 && c->H * cs > c->num_sms) cs >>= 1;
   }
+  // Fused q/k/v+attention per head, measured on 7B at 2 ranks: clusters of 8 (128 CTAs) 266 tok/s --
+  // sixteen 8-CTA clusters do not all become resident at once --, clusters of 4 (64 CTAs) 309.5,
+  // stand-alone kernels 302.8.  With 4 or 8 ranks a rank owns too few heads to fill its SMs with one
+  // cluster per head: those keep the stand-alone kernels unless fuse_cluster is set explicitly.
+  int fcs = c->opt.fuse_cluster > 0 ? c->opt.fuse_cluster : (Hl * 8 <= 96 ? 8 : 4);
+  while (fcs > 1 && (Hl * fcs > c->num_sms || 3 * hs / 2 < fcs)) fcs >>= 1;
+  const bool fuse = c->opt.fuse_qkv_attn && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64 &&
+                    (G <= 2 || c->opt.fuse_cluster > 0);
   for (int l = 0; l < L; ++l) {
     const int eA = 4 * l, eB = 4 * l + 1, eC = 4 * l + 2, eD = 4 * l + 3;
+    if (fuse) {  // this rank's heads: q/k/v rows + attention in one cluster kernel per head
+      QkvAttnParams f;
+      memset(&f, 0, sizeof f);
+      f.W = c->wqkv + (size_t)l * 3 * Dl * D;
+      f.D = D; f.H = Hl; f.hs = hs; f.steps = c->steps;
+      f.seg_rows = Dl;
+      f.vin = c->x;
+      f.rms_w = c->rms_att + (size_t)l * D;
+      f.tok_emb = (l == 0) ? c->tok_emb : nullptr;
+      f.tokp = c->d_ctl + CTL_HDR;
+      f.posp = c->d_ctl + CTL_HDR + 1;
+      f.x = c->x;
+      f.q = c->q;
+      f.kc = c->kc + (size_t)l * kv_seq;
+      f.vc = c->vc + (size_t)l * kv_seq;
+      f.fcr = c->fcr; f.fci = c->fci;
+      f.xb = c->xb;
+      f.tileT = kAttnStageBytes / (hs * 4);
+      f.sc_cap = ((c->steps + fcs - 1) / fcs + 3) & ~3;
+      f.evict_first = ef;
+      f.l2_prefetch = 0;
+      f.tp_size = G;
+      f.tp_ll_in = l == 0 ? 0 : 1;
+      f.tp_epoch = c->tp_epoch;
+      f.tp_wait_idx = l == 0 ? 0 : eD - 4;
+      f.tp_out_idx = eA;
+      f.xb_off = R * Dl;
+      f.tp_err = c->tp_err;
+      for (int g = 0; g < G; ++g) f.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
+      const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
+      void* args[] = {&f};
+      int rc = launch(c, L2B_K_QKV, (const void*)qkv_attn_tp_kernel, dim3(fcs, Hl, 1), dim3(kFThreads), smem, fcs,
+                      args, st);
+      if (rc) return rc;
+    } else {
     {  // rmsnorm -> this rank's heads of q,k,v -> RoPE -> KV write (needs x from every rank)
       GemvParams p = base;
       p.W = c->wqkv + (size_t)l * 3 * Dl * D;
@@ -724,6 +768,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       int rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, Hl, 1), dim3(kAttnThreads), smem,
                       cs, args, st);
       if (rc) return rc;
+    }
     }
     {  // rows [R*Dl, (R+1)*Dl) of wo + residual -> every replica of x
       GemvParams p = base;
@@ -844,7 +889,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
 
   const int cs = auto_cluster(c, B);
   // fused q/k/v + attention: one cluster per head
-  int fcs = 8;
+  int fcs = c->opt.fuse_cluster > 0 ? c->opt.fuse_cluster : (c->H * 8 <= 96 ? 8 : 4);
   while (fcs > 1 && (c->H * fcs > c->num_sms || 3 * hs / 2 < fcs)) fcs >>= 1;
   const bool fuse = c->opt.fuse_qkv_attn && B == 1 && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64;
   c->sync_idx = -1;
@@ -859,6 +904,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       memset(&f, 0, sizeof f);
       f.W = c->wqkv + (size_t)l * 3 * D * D;
       f.D = D; f.H = H; f.hs = hs; f.steps = c->steps;
+      f.seg_rows = D;
       f.vin = c->x;
       f.rms_w = c->rms_att + (size_t)l * D;
       f.tok_emb = (l == 0) ? c->tok_emb : nullptr;
@@ -2014,6 +2060,9 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.attn_prefetch = v != 0;
   } else if (k == "soft_sync") {
     o.soft_sync = v != 0;
+  } else if (k == "fuse_cluster") {
+    if (v != 0 && v != 1 && v != 2 && v != 4 && v != 8) return fail(c, L2B_EINVAL, "fuse_cluster must be 0, 1, 2, 4 or 8");
+    o.fuse_cluster = v;
   } else if (k == "fuse_prefetch") {
     o.fuse_prefetch = v < 0 ? 0 : (v > 100 ? 100 : v);
   } else if (k == "fuse_qkv_attn") {
