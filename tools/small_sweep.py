@@ -16,7 +16,8 @@ for arch in ("stories15M", "stories42M", "stories110M"):
     torch.cuda.synchronize()
     n = min(hdr[6] - 1, 200)
     base = {"threads": 512, "ctas_per_sm": 1, "l2_prefetch": 262144, "evict_first": -1, "attn_cluster": 0, "pdl": 1}
-    for opts in ({}, {"threads": 256}, {"threads": 256, "ctas_per_sm": 2}, {"l2_prefetch": 0}, {"l2_prefetch": 65536},
+    base.update({"fuse_cluster": 0, "fuse_qkv_attn": 1})
+    for opts in ({}, {"fuse_cluster": 4}, {"fuse_cluster": 2}, {"fuse_cluster": 8}, {"fuse_qkv_attn": 0}, {"threads": 256}, {"threads": 256, "ctas_per_sm": 2}, {"l2_prefetch": 0}, {"l2_prefetch": 65536},
                  {"attn_cluster": 1}, {"attn_cluster": 2}, {"attn_cluster": 4}, {"pdl": 0}, {"threads": 256, "l2_prefetch": 0}):
         cfg = dict(base); cfg.update(opts)
         for k, v in cfg.items():
