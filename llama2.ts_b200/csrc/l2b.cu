@@ -891,7 +891,10 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   // fused q/k/v + attention: one cluster per head
   int fcs = c->opt.fuse_cluster > 0 ? c->opt.fuse_cluster : (c->H * 8 <= 96 ? 8 : 4);
   while (fcs > 1 && (c->H * fcs > c->num_sms || 3 * hs / 2 < fcs)) fcs >>= 1;
-  const bool fuse = c->opt.fuse_qkv_attn && B == 1 && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64;
+  const size_t fuse_smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes +
+                           (size_t)((((c->steps + fcs - 1) / fcs + 3) & ~3)) * 4;
+  const bool fuse = c->opt.fuse_qkv_attn && B == 1 && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64 &&
+                    fuse_smem <= 200 * 1024;
   c->sync_idx = -1;
   if (fuse && c->opt.soft_sync && 4 * c->L + 1 <= c->work_cap) {
     CU(c, cudaMemsetAsync(c->d_sync, 0, sizeof(int) * (size_t)c->work_cap, st));
