@@ -458,7 +458,7 @@ def main():
         "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-        "dtype": "f32 storage, f64 accumulate" if B < 9 else "f32 storage, 3xTF32 tensor-core products, f32 accumulate",
+        "dtype": "f32 storage, f64 accumulate" if B < 3 else "f32 storage, 3xTF32 tensor-core products, f32 accumulate",
         "data": "synthetic", "config": base_cfg,
         "e2e": {"value": n_tok / e2e_s, "unit": "tokens/s",
                 "h2d_bytes_per_step": 4 * (4 + 2 * B), "d2h_bytes_per_step": 4 * B,

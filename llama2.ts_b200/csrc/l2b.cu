@@ -45,7 +45,9 @@ struct Options {
   int ctas_per_sm = 1;
   int attn_cluster = 0;  // 0 = auto
   int evict_first = -1;  // -1 = auto (weights > L2)
-  int tc_min_batch = 5;  // batches >= this run the tcgen05 GEMM path (0 = never)
+  int tc_min_batch = 3;  // batches >= this run the tcgen05 GEMM path (0 = never).  Measured on 7B: 2 sequences
+                         // 5.34 ms/step on the fp64 GEMV path (one weight pass for both); 4 sequences 7.8 ms there
+                         // against 5.8 ms on the tensor-core path
   int tc_splits = 0;     // 0 = auto k-split per GEMM
   int tc_rewrite_hi = 0; // see GemmParams::rewrite_hi
   int attn_warp = 2048;  // batched path: one-warp-per-(sequence, head) attention kernel when there are at
@@ -1450,7 +1452,7 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
   const size_t max_grid = (size_t)c->num_sms * 4;
   TRY(dev_alloc(c, &c->blk_val, max_grid * kMaxNB, true));
   TRY(dev_alloc(c, &c->blk_idx, max_grid * kMaxNB, true));
-  if (max_batch >= 5) {
+  if (max_batch >= 3) {
     // tensor-core path scratch: activations padded to whole 256-column groups
     c->Bpad = ((max_batch + 255) / 256) * 256;
     const size_t Mmax = (size_t)(3 * D > 2 * F ? 3 * D : 2 * F) > sV ? (size_t)(3 * D > 2 * F ? 3 * D : 2 * F) : sV;

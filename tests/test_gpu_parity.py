@@ -210,10 +210,10 @@ def test_variants_agree(pkg, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("B,tc", [(2, 0), (3, 0), (5, 0), (8, 0), (11, 0), (5, 5), (11, 5)])
+@pytest.mark.parametrize("B,tc", [(2, 0), (3, 0), (5, 0), (8, 0), (11, 0), (3, 3), (4, 3), (5, 5), (11, 5)])
 def test_batch_independent_sequences(pkg, oracle, B, tc):
     """B independent RunStates advanced in lock-step but at DIFFERENT positions; tc=0 forces the
-    multi-sequence fp64 GEMV kernels, tc=5 is the default (tensor cores from 5 sequences up)."""
+    multi-sequence fp64 GEMV kernels, tc=3 is the default (tensor cores from 3 sequences up)."""
     hdr = pkg.synth.header("small")
     _, blob = pkg.synth.checkpoint_blob(hdr, seed=9, std=0.05)
     V = abs(hdr[5])
