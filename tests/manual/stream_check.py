@@ -1,6 +1,6 @@
 """Streaming kernel (option mega=2): parity against the oracle, then step time per model.
 
-    python tools/stream_check.py [parity] [time] [7b]
+    python tests/manual/stream_check.py [parity] [time] [7b]
 """
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
