@@ -2,30 +2,43 @@
 """bench.py -- decode tokens/sec of the transformer() hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one decode step (one token) of the named workload: one pass of the hot path
-(llama2.ts:205-303) over one batch.  Default workload: Llama-2-7B architecture, random-init
-fp32, batch-1 greedy decode (BASELINE.json configs[3], the configuration the north_star
-target "batch-1 decode at >= 70% of the HBM roofline" is quoted on).
+A "step" is one decode step (one token per sequence) of the named workload: one pass of the hot
+path (llama2.ts:205-303) over one batch.  Default workload: Llama-2-7B architecture, random-init
+fp32, batch-1 greedy decode (BASELINE.json configs[3], the configuration the north_star target
+"batch-1 decode at >= 70% of the HBM roofline" is quoted on).
 
   value      tokens/s, device-resident greedy loop (inputs in HBM), CUDA-event time on the
              library's stream, max over ranks.
   e2e        tokens/s through the C ABI with HOST buffers: one l2b_forward_argmax(token,pos)
              per token (token+pos copied in from pinned memory, the chosen token copied out),
-             wall clock between device synchronisations, max over ranks.
-  roofline   dominant kernel (w1/w3 matvec + SwiGLU): algorithmic bytes / CUDA-event time per
-             launch, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the CPU oracle (port of the reference forward, oracle/l2ref.c) on 1 host
-             thread -- the reference is single-threaded JS -- over the first tokens.
+             wall clock between device synchronisations, max over ranks.  THE HEADLINE.
+  roofline   dominant kernel: algorithmic bytes / CUDA-event time per launch, against
+             MEASURED_PEAKS.json hbm_gbs; `step` = the whole step's algorithmic bytes / step time.
+  cpu_baseline  the CPU oracle (C restatement of the reference forward, oracle/l2ref.c) on ONE host
+             thread -- the reference is single-threaded JS -- over 16 tokens (N = 1 only).
 
-N > 1: every rank runs its own independent sequence on its own GPU (weights replicated, no
-data-path collective) -- weak scaling; value = N * K tokens / max-over-ranks time.
+N = 1 extras: others (stories15M/42M/110M batch-1), batched (7B with 256 and 32 sequences,
+stories110M with 64: the tcgen05 path), long_context (7B at pos 1792..2047), prefill, sampling, loader.
+
+N > 1 (one process per GPU, torchrun):  the SAME single 7B sequence decoded by ONE tensor-parallel
+group over the N GPUs (BASELINE.json configs[3] "tensor-parallel at 2/4/8 GPUs"; scaling "strong";
+rows of every projection sharded, slices exchanged by peer stores over NVLink inside the kernels).
+Extra keys at every N: `batched` = 256 independent sequences partitioned over the N GPUs
+(configs[4]), `tp_parity` = the tensor-parallel logits against the one-GPU library (bit for bit)
+and the oracle on small shapes + the 7B greedy tokens against the one-GPU library,
+`single_process` = the same tensor-parallel group driven by ONE host thread through
+l2b_create_multi (what the reference's single JS thread would call).
+--replicas restores round 1's weak-scaling mode (one independent sequence per GPU).
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -121,9 +134,9 @@ class ClockSampler:
 
 
 def build_weights_on_gpu(pkg, ctx, hdr, seed, device, keep_host=False):
-    """Random-init weights generated on the GPU (torch = plumbing) and handed to l2b_upload.
-    keep_host=True also returns the checkpoint as one float32 host blob (file order) for the
-    CPU oracle."""
+    """Random-init weights generated on the GPU (torch = plumbing) and handed to l2b_upload
+    (a context group copies from `device` into every member).  keep_host=True also returns the
+    checkpoint as one float32 host blob (file order) for the CPU oracle."""
     import torch
     blob = None
     off = 0
@@ -180,11 +193,19 @@ def host_mem_ok(n_bytes):
     return avail is not None and avail > 1.6 * n_bytes + (8 << 30)
 
 
+def host_threads():
+    """Host threads this process may use.  Counted from the affinity mask, NOT from
+    OMP_NUM_THREADS (torchrun sets that to 1), so the reference arm is the same at every N."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(oracle, hdr, blob, threads, budget_s, max_tokens, warm=0):
     """Times the oracle's decode loop on `threads` host threads; stops at budget_s."""
     m = oracle.Model(hdr, blob)
     oracle.set_threads(threads)
-    V = abs(hdr[5])
     tok = 1
     for p in range(warm):
         tok = int(np.argmax(m.forward(tok, p))) or 2
@@ -202,29 +223,65 @@ def cpu_sample(oracle, hdr, blob, threads, budget_s, max_tokens, warm=0):
     return n / dt, n, dt
 
 
-def run_workload(pkg, name, device, steps, warmup, seed, B=1, keep_host=False, tp=None):
-    """Builds the named architecture on this rank's GPU (random-init weights generated on the
-    device) with B independent sequences; returns (state, loop_device)."""
+def js_reference_probe(pkg):
+    """when a JS runtime AND the reference checkout are on this box, run the
+    reference itself -- `node --experimental-loader=./t348.mjs llama2.ts <ckpt> -t 0 -s 1 -n 256 -i
+    "Once upon a time"` (package.json:10) from a scratch copy -- on a synthetic stories15M-architecture
+    checkpoint (the bundled stories15M.bin is missing from the checkout) and parse `achieved tok/s`
+    (llama2.ts:511).  Returns a dict, or a reason string."""
+    exe = shutil.which("bun") or shutil.which("node")
+    if not exe:
+        return "no node/bun on this box"
+    ref = os.environ.get("L2B_REFERENCE_DIR", "/root/reference")
+    if not os.path.exists(os.path.join(ref, "llama2.ts")):
+        return "%s found but no reference checkout at %s" % (os.path.basename(exe), ref)
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            for f in ("llama2.ts", "t348.mjs", "tokenizer.bin", "package.json", "tsconfig.json"):
+                if os.path.exists(os.path.join(ref, f)):
+                    shutil.copy(os.path.join(ref, f), td)
+            ck = pkg.synth.write_checkpoint(os.path.join(td, "synthetic15M.bin"), pkg.synth.header("stories15M"), seed=0)
+            cmd = [exe, "llama2.ts"] if exe.endswith("bun") else [exe, "--experimental-loader=./t348.mjs", "llama2.ts"]
+            cmd += [ck, "-t", "0", "-s", "1", "-n", "256", "-i", "Once upon a time"]
+            r = subprocess.run(cmd, cwd=td, capture_output=True, text=True, timeout=240)
+            import re
+            m = re.search(r"achieved tok/s:\s*([0-9.]+)", r.stdout + r.stderr)
+            if not m:
+                return "reference ran (rc %d) but printed no tok/s" % r.returncode
+            return {"value": float(m.group(1)), "unit": "tokens/s", "cores": 1, "kind": "reference",
+                    "sample": "the reference's own llama2.ts under %s, stories15M architecture, random-init, "
+                              "-t 0 -s 1 -n 256 -i 'Once upon a time'" % os.path.basename(exe)}
+    except Exception as e:  # a baseline probe must never take the bench down
+        return "reference run failed: %s" % e
+
+
+def run_workload(pkg, name, device, steps, warmup, seed, B=1, keep_host=False, tp=None, max_steps=0, group=None):
+    """Builds the named architecture (random-init weights generated on the device) with B independent
+    sequences; returns (state, loop_device).  tp = (rank, world): one rank of a tensor-parallel group
+    (one process per GPU); group = (n_gpus, tp_degree): a single-process l2b_create_multi context."""
     hdr = pkg.synth.header(name)
     S = hdr[6]
     rows = min(S, warmup + steps)
-    if tp:
-        ctx = pkg.Context(hdr, device=device, max_steps=rows, tp_rank=tp[0], tp_size=tp[1])
+    cap = max(rows, min(S, max_steps))
+    if group:
+        ctx = pkg.Context(hdr, n_gpus=group[0], tp_degree=group[1], max_batch=B, max_steps=cap)
+    elif tp:
+        ctx = pkg.Context(hdr, device=device, max_steps=cap, tp_rank=tp[0], tp_size=tp[1])
     else:
-        ctx = pkg.Context(hdr, device=device, max_batch=B, max_steps=rows)
+        ctx = pkg.Context(hdr, device=device, max_batch=B, max_steps=cap)
     blob = build_weights_on_gpu(pkg, ctx, hdr, seed, "cuda:%d" % device, keep_host)
     if tp:
         pkg.dist.connect_tp(ctx)
     out = {"hdr": hdr, "ctx": ctx, "blob": blob, "rows": rows, "B": B}
     V = abs(hdr[5])
 
-    def loop_device(n, pos0, tok0):
-        """n steps of the device-resident greedy loop (all B sequences), wrapping at the KV
-        capacity.  Returns (device ms, launches, last tokens, next pos)."""
+    def loop_device(n, pos0, tok0, nb=B):
+        """n steps of the device-resident greedy loop (nb sequences), wrapping at `rows`.
+        Returns (device ms, launches, last tokens, next pos)."""
         ms, launches, done, tok, pos = 0.0, 0, 0, np.array(tok0, dtype=np.int32), pos0
         while done < n:
             chunk = min(n - done, rows - pos)
-            toks = ctx.generate_greedy(tok, np.full(B, pos, np.int32), chunk)
+            toks = ctx.generate_greedy(tok, np.full(nb, pos, np.int32), chunk)
             ms += ctx.last_device_ms()
             launches += ctx.last_launches()
             tok = toks[-1].copy()
@@ -236,167 +293,16 @@ def run_workload(pkg, name, device, steps, warmup, seed, B=1, keep_host=False, t
     first = np.ones(B, dtype=np.int32) if B == 1 else pkg.synth.teacher_tokens(B, V, seed + 99)
     _, _, tok, pos = loop_device(warmup, 0, first)
     out["after_warmup"] = (tok, pos)
+    out["first"] = first
     return out, loop_device
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
-    ap.add_argument("--warmup", type=int, default=8)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="llama2-7b")
-    ap.add_argument("--batch", type=int, default=0,
-                    help="GLOBAL number of independent sequences, partitioned over the ranks "
-                         "(strong scaling); 0 = one sequence per GPU (weak scaling, the default)")
-    ap.add_argument("--tp", action="store_true",
-                    help="all ranks form ONE tensor-parallel group decoding a single sequence "
-                         "(row-sharded projections + in-kernel NVLink exchange; strong scaling)")
-    ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-others", action="store_true")
-    ap.add_argument("--opt", action="append", default=[], help="key=value for l2b_set_option")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    import llama2_ts_b200 as pkg
-    from oracle import l2ref as oracle  # checker / CPU baseline only
-
-    hdr = pkg.synth.header(args.workload)
+def kernel_table(pkg, ctx, hdr, B, ppos, world_tp=1):
+    """Per-kernel CUDA-event times (no graph / PDL overlap) of 3 steps at position ppos."""
+    K = pkg.capi
     D, F, L, H = hdr[:4]
     V = abs(hdr[5])
-    if args.batch > 0:
-        assert args.batch % world == 0, "--batch must be divisible by the number of ranks"
-        B = args.batch // world
-        scaling = "strong"
-        par = "%d independent sequences partitioned over %d GPU(s), %d per GPU (weights replicated, " \
-              "no data-path collective)" % (args.batch, world, B)
-    elif args.tp and world > 1:
-        B, scaling = 1, "strong"
-        par = "tensor parallel tp%d: rows of every projection sharded over the ranks, slices exchanged " \
-              "by peer stores over NVLink inside the kernels (4 all-gathers per layer)" % world
-    else:
-        B, scaling = 1, "weak"
-        par = "independent sequences per GPU (weights replicated, no collective)"
-    base_cfg = {"workload": "%s architecture, random-init fp32, %s greedy decode (-t 0), %d steps"
-                            % (args.workload, "batch-1" if B == 1 else "batch-%d/GPU" % B, args.steps),
-                "dim": D, "hidden_dim": F, "n_layers": L, "n_heads": H,
-                "vocab": V, "batch_per_gpu": B, "global_batch": B * world, "parallelism": par,
-                "l2": "inputs larger than L2" if pkg.synth.weight_bytes_per_token(hdr) > 126e6
-                      else "weights fit the 126 MB L2 (L2-resident; HBM fraction is nominal)"}
-
-    # ------------------------------------------------------------------ reference arm
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        oracle.build()
-        threads = oracle.max_threads()
-        if not host_mem_ok(4 * pkg.synth.weight_floats(hdr)):
-            print(json.dumps({"impl": "reference", "unavailable": "host memory too small for the "
-                              "%.1f GB checkpoint" % (4e-9 * pkg.synth.weight_floats(hdr))}))
-            return 0
-        blob = host_blob(pkg, hdr, args.seed)
-        budget = 90.0
-        warm = 1
-        tps, n, dt = cpu_sample(oracle, hdr, blob, threads, budget, args.steps, warm=warm)
-        line = {"impl": "reference", "metric": "decode tokens/sec", "value": tps, "unit": "tokens/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1000.0 / tps, "higher_is_better": True, "scaling": scaling,
-                "vs_baseline": None, "dtype": "f32 storage, f64 accumulate", "data": "synthetic",
-                "config": base_cfg,
-                "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                 "sample": "oracle/l2ref.c (C port of llama2.ts:205-303; no JS runtime "
-                                           "in the image), matmul rows split over %d host threads "
-                                           "(bit-identical to 1 thread), one sequence, %d warm-up + %d "
-                                           "timed tokens from pos %d, %.1f s (time-capped at %.0f s)"
-                                           % (threads, warm, n, warm, dt, budget)},
-                "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
-
-    # ------------------------------------------------------------------ our arm
-    import torch
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the product has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    want_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
-    cpu_skip = None
-    if want_cpu and not host_mem_ok(4 * pkg.synth.weight_floats(hdr)):
-        want_cpu, cpu_skip = False, "host memory too small for a %.1f GB checkpoint copy" % (
-            4e-9 * pkg.synth.weight_floats(hdr))
-    tp = (rank, world) if (args.tp and world > 1) else None
-    st, loop_device = run_workload(pkg, args.workload, local_rank, args.steps, args.warmup,
-                                   args.seed + (0 if tp else rank), B=B, keep_host=want_cpu, tp=tp)
-    ctx, rows = st["ctx"], st["rows"]
-    for kv in args.opt:
-        k, v = kv.split("=")
-        ctx.set_option(k, int(v))
-    if args.opt:
-        loop_device(args.warmup, 0, st["after_warmup"][0])
-    tok, pos = st["after_warmup"]
-
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    # ---- timed region 1: device-resident loop, K steps (inputs already in HBM)
-    barrier()
-    ms, launches, tok2, pos2 = loop_device(args.steps, pos, tok)
-    barrier()
-    ms = max_over_ranks(ms)
-    # ---- timed region 2: end to end through the C ABI, host buffers, one call per step
-    t_tok, t_pos = tok.copy(), pos
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        if B == 1:
-            nxt = ctx.forward_argmax(int(t_tok[0]), t_pos)
-            t_tok[0] = nxt if nxt != 1 else 2
-        else:
-            _, am = ctx.forward_batch(t_tok, np.full(B, t_pos, np.int32), want_logits=False)
-            t_tok = np.where(am == 1, 2, am).astype(np.int32)
-        t_pos = (t_pos + 1) % rows
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    e2e_s = max_over_ranks(e2e_s)
-    # same, returning the full logits to the host (the temperature / top-p path)
-    n_lg = min(args.steps, 32)
-    t0 = time.perf_counter()
-    for _ in range(n_lg):
-        lg, _ = ctx.forward_batch(t_tok, np.full(B, t_pos, np.int32), want_argmax=False)
-        t_tok = np.argmax(lg, axis=1).astype(np.int32)
-        t_tok[t_tok == 1] = 2
-        t_pos = (t_pos + 1) % rows
-    e2e_logits_s = (time.perf_counter() - t0) * args.steps / n_lg
-    clk = clocks.stop()
-
-    # ---- per-kernel CUDA-event times (no graph / PDL overlap), 3 steps mid-sequence
-    K = pkg.capi
-    kms = np.zeros(K.K_COUNT)
-    kn = np.zeros(K.K_COUNT)
-    ppos = min(rows - 5, max(0, args.warmup + args.steps // 2))
+    kms, kn = np.zeros(K.K_COUNT), np.zeros(K.K_COUNT)
     for i in range(4):
         a, b = ctx.profile_batch(np.full(B, 2 + i, np.int32), np.full(B, ppos + i, np.int32))
         if i > 0:
@@ -415,10 +321,8 @@ def main():
     fused_attn = B == 1 and kn[K.K_ATTN] == 0 and kn[K.K_QKV] > 0   # q/k/v rows + attention in one kernel
     if fused_attn:
         kbytes[K.K_QKV] += kv_b
-    if tp:   # every rank streams 1/world of each weight matrix
-        kbytes = {k: v / world for k, v in kbytes.items()}
-    peak, peak_src = peaks()
-    tpeak = tensor_peak()
+    if world_tp > 1:   # every rank streams 1/world of each weight matrix
+        kbytes = {k: v / world_tp for k, v in kbytes.items()}
     per_kernel = {}
     for k in range(K.K_COUNT):
         if kn[k] > 0:
@@ -432,11 +336,18 @@ def main():
                 d["tflops_3xtf32"] = round(3 * kflops[k] / (avg_ms * 1e-3) / 1e12, 1)
             per_kernel[K.KERNEL_NAMES[k] + ("_attention" if (fused_attn and k == K.K_QKV) else "")] = d
     dom = max((k for k in range(K.K_COUNT) if k != K.K_BATCH_EPI), key=lambda k: kms[k])
-    dom_ms = kms[dom] / kn[dom]
+    return per_kernel, dom, kms[dom] / kn[dom], kbytes, kflops
+
+
+def roofline_of(pkg, ctx, hdr, B, ppos, name, world_tp=1):
+    K = pkg.capi
+    peak, peak_src = peaks()
+    tpeak = tensor_peak()
+    per_kernel, dom, dom_ms, kbytes, kflops = kernel_table(pkg, ctx, hdr, B, ppos, world_tp)
     hbm_rate = kbytes[dom] / (dom_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": K.KERNEL_NAMES[dom], "achieved": hbm_rate, "peak": peak,
             "unit": "GB/s", "frac": hbm_rate / peak, "peak_source": peak_src,
-            "traffic": ncu_traffic(K.KERNEL_NAMES[dom]) if (args.workload == "llama2-7b" and B == 1) else None,
+            "traffic": ncu_traffic(K.KERNEL_NAMES[dom]) if (name == "llama2-7b" and B == 1 and world_tp == 1) else None,
             "algorithmic_bytes_per_launch": kbytes[dom], "avg_launch_us": 1000 * dom_ms}
     if dom in kflops:
         tf = 3 * kflops[dom] / (dom_ms * 1e-3) / 1e12
@@ -444,6 +355,213 @@ def main():
                           "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)"}
         if tf / tpeak > hbm_rate / peak:
             roof.update({"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak})
+    roof["per_kernel"] = per_kernel
+    return roof
+
+
+def batched_point(pkg, name, device, B_list, steps, warmup, seed, max_batch):
+    """Batched decode (tcgen05 3xTF32 path) of `name` on one GPU for each B in B_list (one context,
+    weights uploaded once).  Returns {B: {...}}."""
+    peak, _ = peaks()
+    tpeak = tensor_peak()
+    hdr = pkg.synth.header(name)
+    D, F, L, H = hdr[:4]
+    V = abs(hdr[5])
+    st, loop = run_workload(pkg, name, device, steps, warmup, seed, B=max_batch)
+    ctx, rows = st["ctx"], st["rows"]
+    out = {}
+    for B in B_list:
+        ctx.reset()
+        first = pkg.synth.teacher_tokens(B, V, seed + 7)
+        _, _, tok, pos = loop(warmup, 0, first, nb=B)
+        ms, _, _, _ = loop(steps, pos, tok, nb=B)
+        sb = pkg.synth.step_bytes(hdr, pos + (steps - 1) / 2.0, B=B)
+        flops = 3 * 2.0 * (L * (4 * D * D + 3 * D * F) + V * D) * B
+        step_s = ms / steps * 1e-3
+        out["B=%d" % B] = {"tokens_per_s": B * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+                           "step_hbm_frac": sb / step_s / 1e9 / peak,
+                           "step_tensor_frac": flops / step_s / 1e12 / tpeak,
+                           "bound": "tensor" if flops / tpeak / 1e12 > sb / peak / 1e9 else "hbm"}
+    ctx.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def reference_arm(args, pkg, oracle, hdr, base_cfg, scaling):
+    oracle.build()
+    threads = host_threads()
+    if not host_mem_ok(4 * pkg.synth.weight_floats(hdr)):
+        print(json.dumps({"impl": "reference", "unavailable": "host memory too small for the "
+                          "%.1f GB checkpoint" % (4e-9 * pkg.synth.weight_floats(hdr))}))
+        return 0
+    blob = host_blob(pkg, hdr, args.seed)
+    budget, warm = 90.0, 1
+    tps, n, dt = cpu_sample(oracle, hdr, blob, threads, budget, args.steps, warm=warm)
+    tps1, n1, dt1 = cpu_sample(oracle, hdr, blob, 1, 20.0, 4)
+    js = js_reference_probe(pkg)
+    line = {"impl": "reference", "metric": "decode tokens/sec", "value": tps, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / tps, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f32 storage, f64 accumulate", "data": "synthetic",
+            "config": base_cfg,
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                             "sample": "oracle/l2ref.c (C restatement of llama2.ts:205-303; %s), matmul rows "
+                                       "split over %d host threads set explicitly (the affinity mask, not "
+                                       "OMP_NUM_THREADS: identical at every --gpus N; bit-identical to 1 "
+                                       "thread), ONE sequence, %d warm-up + %d timed tokens from pos %d, "
+                                       "%.1f s (time-capped at %.0f s)"
+                                       % (js if isinstance(js, str) else "JS reference timed beside it", threads,
+                                          warm, n, warm, dt, budget),
+                             "single_thread": {"value": tps1, "cores": 1, "tokens": n1, "seconds": dt1,
+                                               "note": "the reference itself is one JS thread (README.md:10-11)"}},
+            "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if isinstance(js, dict):
+        line["js_reference"] = js
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="llama2-7b")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="GLOBAL number of independent sequences, partitioned over the ranks "
+                         "(strong scaling, weights replicated); 0 = the default mode")
+    ap.add_argument("--tp", action="store_true", help="(default for N > 1) all ranks form ONE tensor-parallel group")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N > 1: one independent batch-1 sequence per GPU (weak scaling; round 1's default)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip every extra key (others, batched, long_context ...)")
+    ap.add_argument("--opt", action="append", default=[], help="key=value for l2b_set_option")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import llama2_ts_b200 as pkg
+    from oracle import l2ref as oracle  # checker / CPU baseline only
+
+    hdr = pkg.synth.header(args.workload)
+    D, F, L, H = hdr[:4]
+    V = abs(hdr[5])
+    use_tp = world > 1 and args.batch == 0 and not args.replicas
+    if use_tp and (H % world or F % world or V % (2 * world)):
+        use_tp = False          # shapes the row sharding cannot split: replicas only
+    if args.batch > 0:
+        assert args.batch % world == 0, "--batch must be divisible by the number of ranks"
+        B = args.batch // world
+        scaling = "strong"
+        par = "%d independent sequences partitioned over %d GPU(s), %d per GPU (weights replicated, " \
+              "no data-path collective)" % (args.batch, world, B)
+    elif use_tp:
+        B, scaling = 1, "strong"
+        par = "ONE sequence, tensor parallel tp%d: rows of every projection sharded over the GPUs, slices " \
+              "exchanged by peer stores over NVLink inside the kernels (4 in-kernel all-gathers per layer, no NCCL " \
+              "on the data path)" % world
+    else:
+        B, scaling = 1, "weak"
+        par = "batch-1 on one GPU" if world == 1 else \
+              "replicas only: one independent sequence per GPU (weights replicated, no collective)"
+    base_cfg = {"workload": "%s architecture, random-init fp32, %s greedy decode (-t 0), %d steps"
+                            % (args.workload, "batch-1" if B == 1 else "batch-%d/GPU" % B, args.steps),
+                "dim": D, "hidden_dim": F, "n_layers": L, "n_heads": H,
+                "vocab": V, "batch_per_gpu": B, "global_batch": B * (1 if use_tp else world), "parallelism": par,
+                "l2": "inputs larger than L2" if pkg.synth.weight_bytes_per_token(hdr) > 126e6
+                      else "weights fit the 126 MB L2 (L2-resident; HBM fraction is nominal)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, pkg, oracle, hdr, base_cfg, scaling if world > 1 else "weak")
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_ranks(v, op="max"):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peak, peak_src = peaks()
+    extras = not args.no_others
+    want_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    cpu_skip = None
+    if want_cpu and not host_mem_ok(4 * pkg.synth.weight_floats(hdr)):
+        want_cpu, cpu_skip = False, "host memory too small for a %.1f GB checkpoint copy" % (
+            4e-9 * pkg.synth.weight_floats(hdr))
+    tp = (rank, world) if use_tp else None
+    long_ctx = world == 1 and B == 1 and extras and args.workload == "llama2-7b"
+    st, loop_device = run_workload(pkg, args.workload, local_rank, args.steps, args.warmup,
+                                   args.seed + (0 if tp else rank), B=B, keep_host=want_cpu, tp=tp,
+                                   max_steps=hdr[6] if long_ctx else 0)
+    ctx, rows = st["ctx"], st["rows"]
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    if args.opt:
+        loop_device(args.warmup, 0, st["after_warmup"][0])
+    tok, pos = st["after_warmup"]
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    # ---- timed region 1: device-resident loop, K steps (inputs already in HBM)
+    barrier()
+    ms, launches, tok2, pos2 = loop_device(args.steps, pos, tok)
+    barrier()
+    ms = reduce_ranks(ms)
+    launches = reduce_ranks(float(launches), "sum")
+    # ---- timed region 2: end to end through the C ABI, host buffers, one call per step
+    t_tok, t_pos = tok.copy(), pos
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if B == 1:
+            nxt = ctx.forward_argmax(int(t_tok[0]), t_pos)
+            t_tok[0] = nxt if nxt != 1 else 2
+        else:
+            _, am = ctx.forward_batch(t_tok, np.full(B, t_pos, np.int32), want_logits=False)
+            t_tok = np.where(am == 1, 2, am).astype(np.int32)
+        t_pos = (t_pos + 1) % rows
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = reduce_ranks(e2e_s)
+    # same, returning the full logits to the host (the temperature / top-p path)
+    n_lg = min(args.steps, 32)
+    t0 = time.perf_counter()
+    for _ in range(n_lg):
+        lg, _ = ctx.forward_batch(t_tok, np.full(B, t_pos, np.int32), want_argmax=False)
+        t_tok = np.argmax(lg, axis=1).astype(np.int32)
+        t_tok[t_tok == 1] = 2
+        t_pos = (t_pos + 1) % rows
+    e2e_logits_s = (time.perf_counter() - t0) * args.steps / n_lg
+    clk = clocks.stop()
+
+    ppos = min(rows - 5, max(0, args.warmup + args.steps // 2))
+    roof = roofline_of(pkg, ctx, hdr, B, ppos, args.workload, world if tp else 1)
 
     n_tok = args.steps * (1 if tp else world) * B
     value = n_tok / (ms * 1e-3)
@@ -453,7 +571,6 @@ def main():
     roof["step"] = {"bytes_per_step": sbytes, "achieved": sbytes / step_s / 1e9,
                     "frac": sbytes / step_s / 1e9 / peak,
                     "roofline_tokens_per_s_per_gpu": B * peak * 1e9 / sbytes}
-    roof["per_kernel"] = per_kernel
     line = {
         "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -471,43 +588,115 @@ def main():
         "clocks": clk,
     }
 
-    if B == 1 and not tp:
-        # the prompt as one batched tensor-core pass vs one decode step per token
-        n_pf = min(256, rows)
-        pf_toks = pkg.synth.teacher_tokens(n_pf, V, 5)
-        ctx.reset()
-        ctx.prefill(pf_toks, 0, want_logits=False)          # warm-up (allocates the scratch)
-        ctx.reset()
-        ctx.prefill(pf_toks, 0, want_logits=False)
-        pf_ms = ctx.last_device_ms()
-        line["prefill"] = {"prompt_tokens": int(n_pf), "device_ms": pf_ms,
-                           "tokens_per_s": n_pf / (pf_ms * 1e-3),
-                           "speedup_vs_token_by_token": (ms / args.steps) * n_pf / pf_ms,
-                           "note": "l2b_prefill: all prompt positions in one 3xTF32 tcgen05 pass "
-                                   "(the reference runs one transformer() call per prompt token)"}
+    # =================================================================== N = 1 extras
+    if world == 1 and B == 1 and extras:
+        try:   # the prompt as one batched tensor-core pass vs one decode step per token
+            n_pf = min(256, rows)
+            pf_toks = pkg.synth.teacher_tokens(n_pf, V, 5)
+            ctx.reset()
+            ctx.prefill(pf_toks, 0, want_logits=False)          # warm-up (allocates the scratch)
+            ctx.reset()
+            ctx.prefill(pf_toks, 0, want_logits=False)
+            pf_ms = ctx.last_device_ms()
+            line["prefill"] = {"prompt_tokens": int(n_pf), "device_ms": pf_ms,
+                               "tokens_per_s": n_pf / (pf_ms * 1e-3),
+                               "speedup_vs_token_by_token": (ms / args.steps) * n_pf / pf_ms,
+                               "note": "l2b_prefill: all prompt positions in one 3xTF32 tcgen05 pass "
+                                       "(the reference runs one transformer() call per prompt token)"}
+        except Exception as e:
+            line["prefill"] = {"error": str(e)}
+    if long_ctx:
+        try:   # the KV term of SURVEY 8(d)'s byte formula: 7B at pos 1792..2047 (2.1 GB of cache per token)
+            S = hdr[6]
+            p0, n_lc = S - 256, min(256, max(32, args.steps))
+            ctx.reset()
+            ctx.prefill(pkg.synth.teacher_tokens(p0, V, 6), 0, want_logits=False)   # fills KV rows 0..p0-1
+            ctx.generate_greedy([5], [p0], 8)                                       # warm-up of this graph
+            t = ctx.generate_greedy([7], [p0 + 8], n_lc - 8 if p0 + n_lc <= S else S - p0 - 8)
+            n_run = t.shape[0]
+            lc_ms = ctx.last_device_ms()
+            lb = pkg.synth.step_bytes(hdr, p0 + 8 + (n_run - 1) / 2.0)
+            line["long_context"] = {"pos_from": p0 + 8, "pos_to": p0 + 8 + n_run - 1, "tokens_per_s": n_run / (lc_ms * 1e-3),
+                                    "ms_per_step": lc_ms / n_run, "bytes_per_step": lb,
+                                    "kv_bytes_per_step": lb - pkg.synth.weight_bytes_per_token(hdr),
+                                    "step_hbm_frac": lb / (lc_ms / n_run * 1e-3) / 1e9 / peak,
+                                    "note": "max_steps = seq_len = 2048; KV rows 0..1791 written by l2b_prefill"}
+        except Exception as e:
+            line["long_context"] = {"error": str(e)}
     if want_cpu:
         oracle.build()
-        tps, n, dt = cpu_sample(oracle, hdr, st["blob"], 1, 20.0, 4)
+        tps, n, dt = cpu_sample(oracle, hdr, st["blob"], 1, 75.0, 16)
+        tpsN, nN, dtN = cpu_sample(oracle, hdr, st["blob"], host_threads(), 30.0, 16)
         # parity spot-check of the very workload being timed (first token, full size)
         ctx.reset()
         t0s = np.ones(B, dtype=np.int32)
         got, _ = ctx.forward_batch(t0s, np.zeros(B, np.int32), want_argmax=False)
         want = oracle.Model(hdr, st["blob"])
-        oracle.set_threads(oracle.max_threads())
+        oracle.set_threads(host_threads())
         ref = want.forward(1, 0)
         oracle.set_threads(1)
+        js = js_reference_probe(pkg)
         line["cpu_baseline"] = {
             "value": tps, "unit": "tokens/s", "cores": 1, "kind": "port",
-            "sample": "oracle/l2ref.c (C port of the reference forward; the reference is one JS "
-                      "thread and no JS runtime exists in the image), first %d tokens of one "
-                      "sequence of this workload, %.1f s" % (n, dt),
+            "sample": "oracle/l2ref.c (C restatement of the reference forward; the reference is one JS "
+                      "thread; %s), first %d tokens of one sequence of this workload, %.1f s"
+                      % (js if isinstance(js, str) else "JS reference timed beside it", n, dt),
+            "all_host_threads": {"value": tpsN, "cores": host_threads(), "tokens": nN, "seconds": dtN},
             "parity_vs_gpu_max_abs_logit_diff": float(np.max(np.abs(got - ref[None, :]))),
             "parity_bit_identical_frac": float(np.mean(got == ref[None, :]))}
+        if isinstance(js, dict):
+            line["js_reference"] = js
     elif rank == 0:
         line["cpu_baseline"] = {"value": None, "skipped": cpu_skip or "N > 1 or --no-cpu-baseline"}
-    ctx.close()
+    st["blob"] = None
 
-    if rank == 0 and world == 1 and B == 1 and not args.no_others:
+    # =================================================================== N > 1 extras (tensor-parallel default)
+    if use_tp and extras:
+        par_out = {}
+        try:   # tensor-parallel parity inside the driver-run artefact (the GPU test box has one GPU)
+            par_out = tp_parity(pkg, oracle, dist, rank, world, local_rank, ctx, args)
+        except Exception as e:
+            par_out = {"status": "error", "error": str(e)}
+        line["tp_parity"] = par_out
+    ctx.close()
+    barrier()
+
+    if use_tp and extras:
+        try:   # BASELINE configs[4]: 256 independent sequences partitioned over the N GPUs
+            gb = 256
+            bl = gb // world
+            stb, loopb = run_workload(pkg, args.workload, local_rank, args.steps, args.warmup, args.seed + rank, B=bl)
+            tb, pb = stb["after_warmup"]
+            barrier()
+            msb, _, _, _ = loopb(args.steps, pb, tb)
+            barrier()
+            msb = reduce_ranks(msb)
+            sb = pkg.synth.step_bytes(hdr, pb + (args.steps - 1) / 2.0, B=bl)
+            line["batched"] = {"global_batch": gb, "per_gpu": bl, "tokens_per_s": gb * args.steps / (msb * 1e-3),
+                               "ms_per_step": msb / args.steps,
+                               "step_hbm_frac_per_gpu": sb / (msb / args.steps * 1e-3) / 1e9 / peak,
+                               "parallelism": "independent sequences partitioned over the GPUs, weights replicated, no "
+                                              "data-path collective (tcgen05 3xTF32 path)", "scaling": "strong"}
+            stb["ctx"].close()
+        except Exception as e:
+            line["batched"] = {"error": str(e)}
+        barrier()
+        if rank == 0:
+            try:   # the same tensor-parallel group driven by ONE host thread (l2b_create_multi)
+                stg, loopg = run_workload(pkg, args.workload, 0, args.steps, args.warmup, args.seed, B=1,
+                                          group=(world, world))
+                tg, pg = stg["after_warmup"]
+                msg, _, tokg, _ = loopg(args.steps, pg, tg)
+                line["single_process"] = {"tokens_per_s": args.steps / (msg * 1e-3), "ms_per_step": msg / args.steps,
+                                          "same_tokens_as_one_process_per_gpu": bool(np.array_equal(tokg, tok2)),
+                                          "call": "l2b_create_multi(hdr, n_gpus=%d, tp_degree=%d, 1, steps): one host "
+                                                  "thread, cudaDeviceEnablePeerAccess, no IPC" % (world, world)}
+                stg["ctx"].close()
+            except Exception as e:
+                line["single_process"] = {"error": str(e)}
+        barrier()
+
+    if rank == 0 and world == 1 and B == 1 and extras:
         others = {}
         for name in ("stories15M", "stories42M", "stories110M"):
             if name == args.workload:
@@ -527,15 +716,23 @@ def main():
             except Exception as e:  # never lose the headline line to a side measurement
                 others[name] = {"error": str(e)}
         line["others"] = others
+        batched = {}
+        kb = max(8, min(args.steps, 32))
+        try:   # BASELINE configs[4] / configs[2] on ONE GPU (the tcgen05 path)
+            if args.workload == "llama2-7b":
+                batched["llama2-7b"] = batched_point(pkg, "llama2-7b", local_rank, [256, 32], kb, 4, args.seed, 256)
+            batched["stories110M"] = batched_point(pkg, "stories110M", local_rank, [64], kb, 4, args.seed, 64)
+        except Exception as e:
+            batched["error"] = str(e)
+        line["batched"] = batched
         try:   # temperature / top-p sampling on the device vs logits to the host
-            h4 = pkg.synth.header("stories15M")
             st4, _ = run_workload(pkg, "stories15M", local_rank, 200, 8, args.seed)
             c4 = st4["ctx"]
-            H = pkg.host
+            Hm = pkg.host
             res = {}
             for name in ("host_sampler", "device_sampler"):
                 c4.reset()
-                rng, tok4, lg4 = H.Rng(1), 1, np.empty(32000, dtype=np.float32)
+                rng, tok4, lg4 = Hm.Rng(1), 1, np.empty(32000, dtype=np.float32)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 for p4 in range(200):
@@ -544,8 +741,8 @@ def main():
                     else:
                         c4.forward(tok4, p4, lg4)
                         lg4[:] = (lg4.astype(np.float64) / 0.8).astype(np.float32)
-                        H.softmax(lg4, 0, 32000)
-                        tok4 = H.sample_topp(lg4, 0.9, rng)
+                        Hm.softmax(lg4, 0, 32000)
+                        tok4 = Hm.sample_topp(lg4, 0.9, rng)
                     tok4 = tok4 if tok4 != 1 else 2
                 res[name + "_tokens_per_s"] = 200 / (time.perf_counter() - t0)
             res["note"] = ("stories15M, -t 0.8 -p 0.9, 200 tokens end to end: l2b_forward + the host mirror's "
@@ -555,7 +752,6 @@ def main():
         except Exception as e:
             line["sampling"] = {"error": str(e)}
         try:   # checkpoint loader fast path vs the reference-order per-tensor reads
-            import tempfile
             h3 = pkg.synth.header("stories110M")
             with tempfile.TemporaryDirectory() as td:
                 fpath = pkg.synth.write_checkpoint(os.path.join(td, "m.bin"), h3, seed=1)
@@ -584,6 +780,71 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def tp_parity(pkg, oracle, dist, rank, world, local_rank, ctx7, args):
+    """Every rank: (1) small shapes -- the tensor-parallel logits of 6 teacher-forced steps must equal the
+    one-GPU library's bit for bit (row sharding keeps each output's summation order) and sit inside
+    1e-4 abs / 1e-3 rel of the oracle; (2) the workload itself -- the first greedy tokens of the
+    tensor-parallel group (ctx7) must be the one-GPU library's on the same weights.  Returns the
+    verdict reduced over ranks."""
+    import torch
+    res = {"status": "ok"}
+    bad = []
+    worst = 0.0
+    for arch, steps in (("small", 6), ("wide", 6)):
+        h = pkg.synth.header(arch)
+        if h[3] % world or h[1] % world or abs(h[5]) % (2 * world) or (h[0] // world) % 2:
+            res[arch] = "skipped: shape not divisible by %d ranks" % world
+            continue
+        _, blob = pkg.synth.checkpoint_blob(h, seed=41, std=0.04)
+        Vs = abs(h[5])
+        toks = np.concatenate([[1], pkg.synth.teacher_tokens(steps - 1, Vs, 41)])
+        tpc = pkg.Context(h, device=local_rank, max_steps=steps, tp_rank=rank, tp_size=world)
+        pkg.synth.upload_blob(tpc, h, blob)
+        pkg.dist.connect_tp(tpc)
+        one = pkg.Context(h, device=local_rank, max_steps=steps)
+        pkg.synth.upload_blob(one, h, blob)
+        one.set_option("fuse_qkv_attn", 1 if world <= 2 else 0)   # the kernels the ranks run
+        ref = oracle.Model(h, blob)
+        bits = True
+        for p in range(steps):
+            got = tpc.forward(int(toks[p]), p)
+            bits = bits and bool(np.array_equal(got, one.forward(int(toks[p]), p)))
+            want = ref.forward(int(toks[p]), p)
+            worst = max(worst, float(np.abs(got - want).max()))
+            if not np.allclose(got, want, rtol=1e-3, atol=1e-4):
+                bad.append("%s pos %d outside the tolerance" % (arch, p))
+        if not bits:
+            bad.append("%s: not bit-identical to one GPU" % arch)
+        res[arch] = "bit-identical to 1 GPU, inside 1e-4/1e-3 of the oracle" if bits else "MISMATCH"
+        dist.barrier()
+        tpc.close()
+        one.close()
+    # the 7B group against the one-GPU library on this rank's GPU (greedy tokens; argmax identity)
+    n7 = 12
+    ctx7.reset()
+    a = ctx7.generate_greedy([1], [0], n7)[:, 0]
+    hdr = ctx7.hdr
+    one7 = pkg.Context(hdr, device=local_rank, max_batch=1, max_steps=n7)
+    one7.set_option("fuse_qkv_attn", 1 if world <= 2 else 0)      # the kernels the ranks run
+    build_weights_on_gpu(pkg, one7, hdr, args.seed, "cuda:%d" % local_rank)
+    b = one7.generate_greedy([1], [0], n7)[:, 0]
+    lg_one = one7.read_state(pkg.capi.S_LOGITS)
+    lg_tp = ctx7.read_state(pkg.capi.S_LOGITS)
+    one7.close()
+    same = bool(np.array_equal(a, b))
+    res["workload_greedy_tokens_identical_to_1gpu"] = same
+    res["workload_last_logits_max_abs_diff_vs_1gpu"] = float(np.abs(lg_one - lg_tp).max())
+    if not same:
+        bad.append("7B greedy tokens differ from one GPU")
+    res["max_abs_logit_diff_vs_oracle"] = worst
+    flag = torch.tensor([len(bad)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+    if flag.item() > 0:
+        res["status"] = "FAILED"
+        res["problems_rank0"] = bad
+    return res
 
 
 if __name__ == "__main__":

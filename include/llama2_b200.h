@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define L2B_ABI_VERSION 1
+#define L2B_ABI_VERSION 2
 
 /* error codes */
 #define L2B_OK        0
@@ -71,11 +71,34 @@ typedef struct l2b_ctx l2b_ctx;
 int l2b_create(const int32_t hdr[7], int32_t device, int32_t max_batch,
                int32_t max_steps, l2b_ctx** out);
 
+/* The boundary exactly as SURVEY.md section 8(b) writes it -- l2b_create(hdr, n_gpus, tp_degree,
+ * max_batch, max_steps) -- for the reference's ONE host thread (llama2.ts:468 is a synchronous call
+ * from a single JS thread): the calling thread drives CUDA devices 0..n_gpus-1 itself, no
+ * second process, no IPC handles, no torch.
+ *   tp_degree == 1        the max_batch sequences are partitioned over the GPUs (sequence b lives on
+ *                         GPU b / ceil(max_batch / n_gpus)); weights are replicated by l2b_upload /
+ *                         l2b_load_checkpoint; no collective touches the data path.
+ *   tp_degree == n_gpus   ONE tensor-parallel group decoding one sequence (max_batch must be 1):
+ *                         rows of every projection sharded over the GPUs, slices exchanged by peer
+ *                         stores over NVLink inside the kernels (cudaDeviceEnablePeerAccess).
+ * Every entry point below accepts the returned handle; l2b_tp_export/l2b_tp_connect and
+ * l2b_prefill (tensor-parallel group) do not apply.  l2b_create(hdr, device, ...) remains the
+ * one-GPU form with an explicit device ordinal; l2b_create_tp is the one-process-per-GPU form. */
+int l2b_create_multi(const int32_t hdr[7], int32_t n_gpus, int32_t tp_degree, int32_t max_batch,
+                     int32_t max_steps, l2b_ctx** out);
+
 /* Tensor-parallel variant (row-sharded projections): this
  * process is rank `tp_rank` of `tp_size` (one process per GPU).  Heads, hidden
  * rows and vocab rows are split evenly; uploads still pass the FULL tensor and
  * the library keeps its slice.  Exchange buffers are wired with
- * l2b_tp_export/l2b_tp_connect below.                                          */
+ * l2b_tp_export/l2b_tp_connect below.
+ * RENDEZVOUS: every rank must issue the same sequence of step calls (same token, pos, n_steps),
+ * and must enter each call within the exchange time-out of its peers (option "tp_timeout_ms",
+ * default 20000): a kernel spins on its peers' data for at most that long, then the call fails
+ * with L2B_ECOMM on every rank of the group (the failure is propagated with the step's last
+ * exchange), no token/pos state is advanced and the exchange epoch still moves on, so the same
+ * step can be re-issued by ALL ranks.  Put a host barrier between loading the weights and the
+ * first step (dist.connect_tp does), because load times differ between ranks.                 */
 int l2b_create_tp(const int32_t hdr[7], int32_t device, int32_t max_steps,
                   int32_t tp_rank, int32_t tp_size, l2b_ctx** out);
 
@@ -123,7 +146,15 @@ int l2b_sample_logits(l2b_ctx* ctx, const float* logits_host, double temperature
 
 /* B independent sequences advance one step each (sequence b uses RunState b).
  * tokens[b], pos[b] as above; logits_out (B*vocab floats, host) may be NULL;
- * argmax_out (B ints, host) may be NULL.                                       */
+ * argmax_out (B ints, host) may be NULL.
+ * NUMERICS per path (also l2b_generate_greedy, l2b_profile_batch):
+ *   B <  tc_min_batch (default 3), or max_batch < 3: the reference-exact path -- fp32 storage,
+ *       fp64 accumulation like JS numbers; the same results as B separate l2b_forward calls.
+ *   B >= tc_min_batch on a ctx created with max_batch >= 3: tcgen05 GEMMs with 3xTF32 products,
+ *       fp32 accumulation and an fp32 expf in SwiGLU -- inside the 1e-4 abs / 1e-3 rel tolerance
+ *       but NOT bit-identical to batch-1 calls, and logits depend slightly on B (k-split choice).
+ *       Callers that need bit parity with l2b_forward set option "tc_min_batch" to 0.
+ *   On the tensor-core path hb is not materialised: l2b_read_state(L2B_S_HB) fails with L2B_ESTATE. */
 int l2b_forward_batch(l2b_ctx* ctx, int32_t B, const int32_t* tokens, const int32_t* pos,
                       float* logits_out, int32_t* argmax_out);
 

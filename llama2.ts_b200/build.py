@@ -5,8 +5,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "l2b.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("l2b.cu", "common.cuh", "decode_kernels.cuh", "batch_gemm.cuh", "mega_kernel.cuh", "sampler.cuh", "tokenizer.inl")] + [
-    os.path.join(HERE, "..", "include", "llama2_b200.h")]
+DEPS = [os.path.join(HERE, "..", "include", "llama2_b200.h")]   # + every file under csrc/ (see _deps)
 OUT = os.path.join(HERE, "libllama2_b200.so")
 
 NVCC_FLAGS = [
@@ -37,7 +36,10 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    # L2B_EXPERIMENTS=1 also compiles the persistent-kernel experiments under experiments/
+    # (option "mega"); they are measured slower than the default path and not part of the product
+    extra = ["-DL2B_EXPERIMENTS"] if os.environ.get("L2B_EXPERIMENTS") == "1" else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

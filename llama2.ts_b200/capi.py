@@ -50,6 +50,7 @@ _p = C.c_void_p
 _SIGNATURES = {
     "l2b_create": (C.c_int, [C.POINTER(_i32), _i32, _i32, _i32, C.POINTER(_p)]),
     "l2b_create_tp": (C.c_int, [C.POINTER(_i32), _i32, _i32, _i32, _i32, C.POINTER(_p)]),
+    "l2b_create_multi": (C.c_int, [C.POINTER(_i32), _i32, _i32, _i32, _i32, C.POINTER(_p)]),
     "l2b_upload": (C.c_int, [_p, _i32, _i32, _p, _u64]),
     "l2b_load_checkpoint": (C.c_int, [_p, C.c_char_p, C.POINTER(C.c_double)]),
     "l2b_weights_ready": (C.c_int, [_p]),
@@ -128,9 +129,13 @@ def _ptr(a):
 class Context:
     """One l2b_ctx: weights + RunState(s) + KV cache on one B200."""
 
-    def __init__(self, hdr, device=0, max_batch=1, max_steps=0, lib=None, tp_rank=0, tp_size=1):
+    def __init__(self, hdr, device=0, max_batch=1, max_steps=0, lib=None, tp_rank=0, tp_size=1,
+                 n_gpus=0, tp_degree=1):
         """tp_size > 1: this process is rank `tp_rank` of a row-sharded tensor-parallel group
-        (l2b_create_tp); call tp_export()/tp_connect() (or dist.connect_tp) before the first step."""
+        (l2b_create_tp); call tp_export()/tp_connect() (or dist.connect_tp) before the first step.
+        n_gpus >= 1: single-process multi-GPU context (l2b_create_multi) over devices 0..n_gpus-1:
+        tp_degree == 1 partitions the max_batch sequences, tp_degree == n_gpus is one
+        tensor-parallel group (max_batch 1)."""
         self.lib = lib or Library.get()
         self.hdr = [int(v) for v in hdr]
         assert len(self.hdr) == 7
@@ -143,7 +148,10 @@ class Context:
         h = (_i32 * 7)(*self.hdr)
         out = _p()
         self.tp_rank, self.tp_size = tp_rank, tp_size
-        if tp_size > 1:
+        self.n_gpus = n_gpus
+        if n_gpus >= 1:
+            rc = self.lib.dll.l2b_create_multi(h, n_gpus, tp_degree, max_batch, max_steps, C.byref(out))
+        elif tp_size > 1:
             rc = self.lib.dll.l2b_create_tp(h, device, max_steps, tp_rank, tp_size, C.byref(out))
         else:
             rc = self.lib.dll.l2b_create(h, device, max_batch, max_steps, C.byref(out))

@@ -80,16 +80,6 @@ struct GemmParams {
                   // 0: hi = hardware truncation of the raw tile (saves 16 KB of st.shared per k-block)
 };
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
 // One lane of a CONVERGED warp (cute::elect_one_sync).  Unlike `if (lane == 0)`, the
 // compiler knows the operands computed by the whole warp are uniform and feeds tcgen05 /
 // bulk-copy instructions from uniform registers directly; with `lane == 0` it wrapped every
@@ -167,7 +157,7 @@ struct Ring {
 // operand slot; the long HBM latency is covered by the landing ring.
 template <int N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_3xtf32_kernel(const __grid_constant__ GemmParams p) {
+l2b_tc3x_matmul_kernel(const __grid_constant__ GemmParams p) {
   constexpr int kTileX = N * kBK * 4;
   // N <= 128: the activation tiles travel with the weight tile in the landing ring (deep
   // prefetch of everything; HBM/L2-latency regime).  N = 256 is tensor-bound and its 64 KB of
@@ -474,7 +464,7 @@ gemm_3xtf32_kernel(const __grid_constant__ GemmParams p) {
 // TMEM columns: [0,256) accumulators (2 sets x G pairs of (main | small)), [256,512) A ring.
 template <int N>
 __global__ void __launch_bounds__(kGemmThreadsTmemA, 1)
-gemm_3xtf32_tmemA_kernel(const __grid_constant__ GemmParams p) {
+l2b_tc3x_tmemA_matmul_kernel(const __grid_constant__ GemmParams p) {
   static_assert(N == 32 || N == 64 || N == 128, "tensor-memory A variant: N <= 128");
   constexpr int kTileX = N * kBK * 4;
   constexpr int kLandSlot = kTileA + 2 * kTileX;   // raw weight tile | X_hi | X_lo
@@ -740,7 +730,7 @@ gemm_3xtf32_tmemA_kernel(const __grid_constant__ GemmParams p) {
 
 // Row-major [M][K] -> tile-major pre-swizzled copy used by the GEMMs (one-time, at first
 // batched use; partial tiles are zero-padded).  One thread per 16-byte chunk.
-__global__ void __launch_bounds__(256) tile_major_kernel(const float* __restrict__ W, float* __restrict__ Wt, int M,
+__global__ void __launch_bounds__(256) l2b_tile_major_kernel(const float* __restrict__ W, float* __restrict__ Wt, int M,
                                                          int K, int tiles_m, int kblocks) {
   const size_t n_chunks = (size_t)tiles_m * kblocks * (kBM * kBK / 4);
   for (size_t q = (size_t)blockIdx.x * 256 + threadIdx.x; q < n_chunks; q += (size_t)gridDim.x * 256) {
@@ -902,12 +892,12 @@ __device__ __forceinline__ void bat_resid_rms_body(const BatVecParams& p) {
   }
   if (CLUSTER) cluster_sync_all();  // nobody exits while a peer may still read its partial sum
 }
-__global__ void __launch_bounds__(256) bat_resid_rms_kernel(const __grid_constant__ BatVecParams p) {
+__global__ void __launch_bounds__(256) l2b_bat_resid_rms_kernel(const __grid_constant__ BatVecParams p) {
   griddep_launch_dependents();
   griddep_wait();
   bat_resid_rms_body<false>(p);
 }
-__global__ void __launch_bounds__(256) bat_resid_rms_cluster_kernel(const __grid_constant__ BatVecParams p) {
+__global__ void __launch_bounds__(256) l2b_bat_resid_rms_cluster_kernel(const __grid_constant__ BatVecParams p) {
   griddep_launch_dependents();
   griddep_wait();
   bat_resid_rms_body<true>(p);
@@ -926,7 +916,7 @@ struct BatQkvParams {
 };
 
 // RoPE (llama2.ts:224-235) + KV-cache write (:238-240); one thread per two row pairs (float4).
-__global__ void __launch_bounds__(256) bat_qkv_epi_kernel(const __grid_constant__ BatQkvParams p) {
+__global__ void __launch_bounds__(256) l2b_bat_qkv_epi_kernel(const __grid_constant__ BatQkvParams p) {
   griddep_launch_dependents();
   griddep_wait();
   const int b = blockIdx.y;
@@ -980,7 +970,7 @@ struct BatSwigluParams {
 };
 
 // SwiGLU (llama2.ts:284-289) -> pre-split input of the w2 GEMM; four elements per thread
-__global__ void __launch_bounds__(256) bat_swiglu_kernel(const __grid_constant__ BatSwigluParams p) {
+__global__ void __launch_bounds__(256) l2b_bat_swiglu_kernel(const __grid_constant__ BatSwigluParams p) {
   griddep_launch_dependents();
   griddep_wait();
   const int b = blockIdx.y;
@@ -1026,7 +1016,7 @@ struct BatLogitsParams {
 };
 
 // logits (llama2.ts:302) + argmax (:364-366) + state advance (:471-504); one CTA per sequence
-__global__ void __launch_bounds__(1024) bat_logits_kernel(const __grid_constant__ BatLogitsParams p) {
+__global__ void __launch_bounds__(1024) l2b_bat_logits_kernel(const __grid_constant__ BatLogitsParams p) {
   __shared__ float s_v[32];
   __shared__ int s_i[32];
   griddep_launch_dependents();
@@ -1074,7 +1064,7 @@ __global__ void __launch_bounds__(1024) bat_logits_kernel(const __grid_constant_
 
 // advances the step counter once every sequence has been handled (own launch: the
 // per-sequence CTAs above must all have read the old value first)
-__global__ void bat_step_kernel(int* ctl) {
+__global__ void l2b_bat_step_kernel(int* ctl) {
   griddep_launch_dependents();
   griddep_wait();
   if (threadIdx.x == 0 && ctl[CTL_ADVANCE]) ctl[CTL_STEP] = ctl[CTL_STEP] + 1;

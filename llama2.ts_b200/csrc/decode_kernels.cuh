@@ -1,12 +1,12 @@
 // decode_kernels.cuh -- decode step of llama2.ts transformer() (llama2.ts:205-303)
 // as five fused sm_100a kernels per layer + a classifier.
 //
-//   gemv_pairs_kernel<PRO_RMS , EPI_QKV   >  rmsnorm -> wq/wk/wv matvec -> RoPE -> KV write
-//   attn_decode_kernel                       scores / softmax / weighted sum, one cluster per head
-//   gemv_pairs_kernel<PRO_COPY, EPI_RESID >  wo matvec + residual
-//   gemv_pairs_kernel<PRO_RMS , EPI_SWIGLU>  rmsnorm -> w1/w3 matvec -> SiLU * gate
-//   gemv_pairs_kernel<PRO_COPY, EPI_RESID >  w2 matvec + residual
-//   gemv_pairs_kernel<PRO_RMS , EPI_LOGITS>  final rmsnorm -> wcls matvec -> device argmax
+//   l2b_rowpair_matvec_kernel<PRO_RMS , EPI_QKV   >  rmsnorm -> wq/wk/wv matvec -> RoPE -> KV write
+//   l2b_attn_decode_kernel                       scores / softmax / weighted sum, one cluster per head
+//   l2b_rowpair_matvec_kernel<PRO_COPY, EPI_RESID >  wo matvec + residual
+//   l2b_rowpair_matvec_kernel<PRO_RMS , EPI_SWIGLU>  rmsnorm -> w1/w3 matvec -> SiLU * gate
+//   l2b_rowpair_matvec_kernel<PRO_COPY, EPI_RESID >  w2 matvec + residual
+//   l2b_rowpair_matvec_kernel<PRO_RMS , EPI_LOGITS>  final rmsnorm -> wcls matvec -> device argmax
 //
 // All GEMV phases share one shape: a persistent grid (a multiple of the SM
 // count), each CTA owning a contiguous, balanced range of ROW PAIRS of a
@@ -70,16 +70,27 @@ struct TpParams {
   int* peer_am_idx[kMaxTp];
 };
 
-// bounded spin on a flag written by a peer (about 2 s, then the error word is set so that the
-// host reports L2B_ECOMM instead of hanging the GPU)
+// Bounded spins of the exchange.  The error word `err` is followed in memory by the time-out in
+// units of 2^20 clocks (option "tp_timeout_ms", default 20 s): when a peer's data does not show
+// up in time the word is set and the host reports L2B_ECOMM instead of hanging the GPU.  Once it
+// is set, every later wait of the step gives up after a few polls (a void step costs
+// microseconds, not 129 time-outs), and l2b_tp_finalize_kernel still moves the exchange epoch on,
+// so all ranks stay in lockstep and the host can re-issue the step.
+__device__ __forceinline__ bool tp_spin_expired(long long t0, int* err, int& polls) {
+  if ((++polls & 63) != 0) return false;
+  if (ld_act_i32(err) != 0) return true;
+  if (clock64() - t0 > ((long long)ld_act_i32(err + 1) << 20)) {
+    atomicExch(err, 1);
+    return true;
+  }
+  return false;
+}
 __device__ __forceinline__ void tp_wait_flag(const int* f, int seq, int* err) {
   const long long t0 = clock64();
+  int polls = 0;
   while (ld_acquire_sys_i32(f) < seq) {
     __nanosleep(40);
-    if (clock64() - t0 > 4000000000LL) {
-      atomicExch(err, 1);
-      break;
-    }
+    if (tp_spin_expired(t0, err, polls)) break;
   }
 }
 
@@ -104,11 +115,9 @@ __device__ __forceinline__ float4 ll_load4(const void* base, int j, bool check, 
   uint4 a = ld_volatile_u4(b4), b = ld_volatile_u4(b4 + 1);
   if (check) {
     const long long t0 = clock64();
+    int polls = 0;
     while (!((int)a.y == seq && (int)a.w == seq && (int)b.y == seq && (int)b.w == seq)) {
-      if (clock64() - t0 > 4000000000LL) {
-        atomicExch(err, 1);
-        break;
-      }
+      if (tp_spin_expired(t0, err, polls)) break;
       a = ld_volatile_u4(b4);
       b = ld_volatile_u4(b4 + 1);
     }
@@ -241,7 +250,7 @@ __device__ __forceinline__ void argmax_consider(float v, int i, float& bv, int& 
 
 template <int PRO, int EPI, int NB, int THREADS, bool F64, bool TP = false>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 && NB <= 2) ? 2 : 1)
-gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
+l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
   constexpr int WARPS = THREADS / 32;
   constexpr int KACC = (NB == 1) ? 2 : 1;  // independent FMA chains per (row, sequence)
   typedef XVec<F64> XV;
@@ -569,7 +578,7 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
     }
     __syncthreads();
     if (TP) {
-      // rank-local candidate -> every peer; tp_finalize_kernel picks the global first maximum
+      // rank-local candidate -> every peer; l2b_tp_finalize_kernel picks the global first maximum
       if (s_is_last && warp == 0) {
         __threadfence();
         float v = -INFINITY;
@@ -582,6 +591,7 @@ gemv_pairs_kernel(const __grid_constant__ GemvParams p) {
           const int oi = __shfl_xor_sync(0xffffffffu, i, o);
           argmax_consider(ov, oi, v, i);
         }
+        if (ld_act_i32(p.tp.err) != 0) i = -1;  // poison: every rank learns that this step is void
         if (lane < p.tp.size) {
           st_relaxed_sys_f32(p.tp.peer_am_val[lane] + p.tp.rank, v);
           asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.tp.peer_am_idx[lane] + p.tp.rank), "r"(i)
@@ -678,14 +688,14 @@ struct AttnParams {
   float* xh;
   float* xl;
   int x_npad;
-  int nbatch;        // attn_warp_kernel: number of batch entries
+  int nbatch;        // l2b_attn_warp_kernel: number of batch entries
   // attention is latency-bound and leaves HBM idle: meanwhile pull the NEXT kernel's weights
   // (wo of this layer) into L2
   const unsigned char* pf_ptr;
   long long pf_bytes;
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 1) l2b_attn_decode_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(128) unsigned char attn_smem_raw[];
   float* ring = reinterpret_cast<float*>(attn_smem_raw);                      // kAttnStages * stage
   float* sc = ring + (size_t)kAttnStages * (kAttnStageBytes / 4);          // sc_cap floats
@@ -920,7 +930,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
 // form (global max, f32-rounded exponentials, f64 sum).  Scores live in shared memory.
 constexpr int kAttnWarpThreads = 256;
 constexpr int kAttnWarpRows = 8;   // cache rows in flight per warp (head_size <= 128: one float4 per lane)
-__global__ void __launch_bounds__(kAttnWarpThreads) attn_warp_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kAttnWarpThreads) l2b_attn_warp_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(16) float attn_warp_sc[];  // [warps][sc_cap]
   griddep_launch_dependents();
   griddep_wait();
@@ -1024,14 +1034,15 @@ struct TpFinalParams {
   int* out_tokens;
   int* err;
 };
-__global__ void tp_finalize_kernel(const __grid_constant__ TpFinalParams p) {
+__global__ void l2b_tp_finalize_kernel(const __grid_constant__ TpFinalParams p) {
   griddep_launch_dependents();
   griddep_wait();
   const int lane = threadIdx.x;
   const int base = ld_act_i32(p.epoch);
   if (lane < p.size) tp_wait_flag(p.wait_flags + lane, base + 1 + p.wait_idx, p.err);
+  if (lane < p.size && ld_act_i32(p.am_idx + lane) == -1) atomicExch(p.err, 1);  // a peer timed out
   __syncwarp();
-  if (lane == 0) {
+  if (lane == 0 && ld_act_i32(p.err) == 0) {   // a timed-out step changes no host-visible state
     float v = -INFINITY;
     int i = 0x7fffffff;
     for (int g = 0; g < p.size; ++g) argmax_consider(ld_act(p.am_val + g), ld_act_i32(p.am_idx + g), v, i);
@@ -1050,6 +1061,8 @@ __global__ void tp_finalize_kernel(const __grid_constant__ TpFinalParams p) {
       p.ctl[CTL_HDR + 1] = p.ctl[CTL_HDR + 1] + 1;
       p.ctl[CTL_STEP] = step + 1;
     }
+  }
+  if (lane == 0) {   // the epoch moves on even after a time-out: ranks stay in lockstep
     *p.epoch = base + p.n_exchanges;
   }
 }

@@ -5,7 +5,7 @@
 // head computes that head's 3*head_size rows (split over the cluster's CTAs, same row-pair
 // GEMV as decode_kernels.cuh), hands q and the new k/v row to every CTA of the cluster through
 // distributed shared memory, and after one cluster barrier runs the attention of that head
-// split over time (exact two-pass softmax through DSMEM, as attn_decode_kernel).  That removes
+// split over time (exact two-pass softmax through DSMEM, as l2b_attn_decode_kernel).  That removes
 // one of the five kernel boundaries of a layer (~6 us each on Llama-2-7B, 32 per token) and
 // the attention kernel's own start-up; the K/V rows of earlier positions are requested with
 // bulk async copies right after griddepcontrol.wait, so they land while the GEMV part runs.
@@ -481,10 +481,10 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
   cluster_sync_all();  // keep every CTA's shared memory alive until rank 0 has read it
   if (p.sync_done != nullptr) soft_signal(p.sync_done);
 }
-__global__ void __launch_bounds__(kFThreads, 1) qkv_attn_kernel(const __grid_constant__ QkvAttnParams p) {
+__global__ void __launch_bounds__(kFThreads, 1) l2b_qkv_attn_kernel(const __grid_constant__ QkvAttnParams p) {
   qkv_attn_body<false>(p);
 }
-__global__ void __launch_bounds__(kFThreads, 1) qkv_attn_tp_kernel(const __grid_constant__ QkvAttnParams p) {
+__global__ void __launch_bounds__(kFThreads, 1) l2b_qkv_attn_tp_kernel(const __grid_constant__ QkvAttnParams p) {
   qkv_attn_body<true>(p);
 }
 

@@ -24,8 +24,10 @@
 #include "../../include/llama2_b200.h"
 #include "batch_gemm.cuh"
 #include "decode_kernels.cuh"
-#include "mega_kernel.cuh"
-#include "stream_kernel.cuh"
+#ifdef L2B_EXPERIMENTS  // persistent-kernel experiments (measured slower; built only on request)
+#include "../../experiments/mega_kernel.cuh"
+#include "../../experiments/stream_kernel.cuh"
+#endif
 #include "fused_qkv_attn.cuh"
 #include "sampler.cuh"
 
@@ -52,7 +54,7 @@ struct Options {
   int tc_rewrite_hi = 0; // see GemmParams::rewrite_hi
   int attn_warp = 2048;  // batched path: one-warp-per-(sequence, head) attention kernel when there are at
                          // least this many (sequence, head) pairs (0 = never); below, the cluster kernel
-  int tc_tmem_a = 1;     // N <= 128: weight operand in tensor memory (gemm_3xtf32_tmemA_kernel)
+  int tc_tmem_a = 1;     // N <= 128: weight operand in tensor memory (l2b_tc3x_tmemA_matmul_kernel)
   int dyn_sched = 0;         // batch-1 GEMV kernels hand out row pairs dynamically (see GemvParams::work);
                              // measured: CTAs finish together, but 193 vs 199 tok/s -- under PDL the next
                              // kernel's prefetch already fills the SMs that finish early
@@ -68,6 +70,7 @@ struct Options {
   int fuse_cluster = 0;  // CTAs per head of the fused kernel (0 = largest of 8/4/2/1 that fits the SMs)
   int fuse_prefetch = 0; // ... optionally pulling this percentage of wo into L2 while its attention part runs
                          // (measured net-negative: wo 20.0 -> 16.6 us but the fused kernel 46.0 -> 50.6 us)
+  int tp_timeout_ms = 20000; // tensor-parallel exchange: bounded spin (see tp_spin_expired)
   int stream_stages = 0; // mega=2: ring stages per warp (0 = as many as shared memory holds)
   int stream_chunks = 0; // mega=2: attention time chunks per head (0 = SMs / heads, at most 8)
                          // (experiment, opt-in: measured slower than graph+PDL so far)
@@ -127,10 +130,10 @@ struct l2b_ctx {
   int dbg_arm = 0;
   float* Wt = nullptr;       // tile-major copy of every projection (built at first batched use)
   bool wt_dirty = true;      // weights changed since the copy was built
+  bool last_tc = false;      // the last step ran on the tensor-core path (hb is never materialised there)
   std::vector<size_t> wt_off; // float offsets: per layer {qkv, wo, w13, w2}, then cls
   size_t P_floats = 0;
   int Bpad = 0, Smax = 8;
-  std::map<std::pair<const void*, int>, CUtensorMap> tmaps;  // key: (operand base, box rows)
   // host staging (pinned)
   int* h_ctl = nullptr;
   float* h_logits = nullptr;
@@ -150,6 +153,12 @@ struct l2b_ctx {
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
   std::vector<int> prof_class;
+  // single-process multi-GPU group (l2b_create_multi): this ctx is only a handle, the members own
+  // the devices.  tp group: every member is one rank, batch 1.  Otherwise sequence b of the global
+  // batch lives on member b / per_kid at local index b % per_kid (weights replicated).
+  std::vector<l2b_ctx*> kids;
+  int per_kid = 0;
+  bool peer_ipc = false;   // peer[] entries were opened with cudaIpcOpenMemHandle (one process per GPU)
   std::string err;
 };
 
@@ -191,6 +200,19 @@ int dev_alloc(l2b_ctx* c, T** p, size_t count, bool zero) {
   return 0;
 }
 
+// tensor-parallel exchange time-out -> device word after the error word, in units of 2^20 clocks
+int write_tp_timeout(l2b_ctx* c) {
+  if (c->tp_size <= 1 || !c->tp_err) return 0;
+  int khz = 1965000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+  long long units = ((long long)c->opt.tp_timeout_ms * khz) >> 20;
+  if (units < 1) units = 1;
+  if (units > 0x7fffffffLL) units = 0x7fffffffLL;
+  const int u = (int)units;
+  CU(c, cudaMemcpy(c->tp_err + 1, &u, sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 void drop_graphs(l2b_ctx* c) {
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
   c->graphs.clear();
@@ -204,8 +226,8 @@ template <int PRO, int EPI>
 gemv_fn pick_gemv(int nb, int threads, bool f64) {
 #define L2B_PICK(NB_, T_)                                             \
   if (nb == NB_ && threads == T_)                                     \
-    return f64 ? (gemv_fn)gemv_pairs_kernel<PRO, EPI, NB_, T_, true>  \
-               : (gemv_fn)gemv_pairs_kernel<PRO, EPI, NB_, T_, false>;
+    return f64 ? (gemv_fn)l2b_rowpair_matvec_kernel<PRO, EPI, NB_, T_, true>  \
+               : (gemv_fn)l2b_rowpair_matvec_kernel<PRO, EPI, NB_, T_, false>;
   L2B_PICK(1, 256)
   L2B_PICK(1, 512)
   L2B_PICK(2, 256)
@@ -229,11 +251,11 @@ gemv_fn pick_kernel(int kc, int nb, int threads, bool f64) {
 
 gemv_fn pick_kernel_tp(int kc) {
   switch (kc) {
-    case L2B_K_QKV: return (gemv_fn)gemv_pairs_kernel<PRO_RMS, EPI_QKV, 1, 512, true, true>;
+    case L2B_K_QKV: return (gemv_fn)l2b_rowpair_matvec_kernel<PRO_RMS, EPI_QKV, 1, 512, true, true>;
     case L2B_K_WO:
-    case L2B_K_W2: return (gemv_fn)gemv_pairs_kernel<PRO_COPY, EPI_RESID, 1, 512, true, true>;
-    case L2B_K_W13: return (gemv_fn)gemv_pairs_kernel<PRO_RMS, EPI_SWIGLU, 1, 512, true, true>;
-    case L2B_K_CLS: return (gemv_fn)gemv_pairs_kernel<PRO_RMS, EPI_LOGITS, 1, 512, true, true>;
+    case L2B_K_W2: return (gemv_fn)l2b_rowpair_matvec_kernel<PRO_COPY, EPI_RESID, 1, 512, true, true>;
+    case L2B_K_W13: return (gemv_fn)l2b_rowpair_matvec_kernel<PRO_RMS, EPI_SWIGLU, 1, 512, true, true>;
+    case L2B_K_CLS: return (gemv_fn)l2b_rowpair_matvec_kernel<PRO_RMS, EPI_LOGITS, 1, 512, true, true>;
   }
   return nullptr;
 }
@@ -344,39 +366,6 @@ int auto_cluster(const l2b_ctx* c, int B) {
 }
 
 // ---- batched tensor-core path --------------------------------------------------
-typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-
-// 2-D fp32 tensor map over a row-major [rows][K] matrix, box = 32 floats x box_rows, 128B swizzle
-int get_tmap(l2b_ctx* c, const float* base, size_t rows, size_t K, int box_rows, const CUtensorMap** out) {
-  const std::pair<const void*, int> key(base, box_rows);
-  auto it = c->tmaps.find(key);
-  if (it == c->tmaps.end()) {
-    static encode_tiled_fn enc = nullptr;
-    if (!enc) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qr;
-      CU(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
-      if (!fn || qr != cudaDriverEntryPointSuccess) return fail(c, L2B_ECUDA, "cuTensorMapEncodeTiled not found");
-      enc = (encode_tiled_fn)fn;
-    }
-    CUtensorMap tm;
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(c, L2B_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    it = c->tmaps.emplace(key, tm).first;
-  }
-  *out = &it->second;
-  return 0;
-}
-
 int gemm_n_for(int cols) { return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256; }
 
 // k-split so that (tiles x splits) fills whole waves of the 148 SMs without drowning the
@@ -420,17 +409,17 @@ int launch_gemm(l2b_ctx* c, int kclass, const float* Wt, int M, int K, const flo
     g.rewrite_hi = c->opt.tc_rewrite_hi;
     g.dl = (224 * 1024 - g.dop * op_slot) / land_slot;
     if (g.dl > 12) g.dl = 12;
-    const void* fn = N == 32 ? (const void*)gemm_3xtf32_kernel<32>
-                   : N == 64 ? (const void*)gemm_3xtf32_kernel<64>
-                   : N == 128 ? (const void*)gemm_3xtf32_kernel<128>
-                              : (const void*)gemm_3xtf32_kernel<256>;
+    const void* fn = N == 32 ? (const void*)l2b_tc3x_matmul_kernel<32>
+                   : N == 64 ? (const void*)l2b_tc3x_matmul_kernel<64>
+                   : N == 128 ? (const void*)l2b_tc3x_matmul_kernel<128>
+                              : (const void*)l2b_tc3x_matmul_kernel<256>;
     size_t smem_bytes = (size_t)g.dl * land_slot + (size_t)g.dop * op_slot + 1024;
     int threads = kGemmThreads;
     if (c->opt.tc_tmem_a && N <= 128) {
       // weight operand in tensor memory: no operand ring in shared memory, all of it is landing ring
-      fn = N == 32 ? (const void*)gemm_3xtf32_tmemA_kernel<32>
-         : N == 64 ? (const void*)gemm_3xtf32_tmemA_kernel<64>
-                   : (const void*)gemm_3xtf32_tmemA_kernel<128>;
+      fn = N == 32 ? (const void*)l2b_tc3x_tmemA_matmul_kernel<32>
+         : N == 64 ? (const void*)l2b_tc3x_tmemA_matmul_kernel<64>
+                   : (const void*)l2b_tc3x_tmemA_matmul_kernel<128>;
       g.dl = (224 * 1024) / land_slot;
       if (g.dl > 12) g.dl = 12;
       smem_bytes = (size_t)g.dl * land_slot + 1024;
@@ -481,9 +470,9 @@ int ensure_tc_weights(l2b_ctx* c) {
   }
   auto conv = [&](const float* W, size_t off, int M, int K) -> int {
     const int tiles_m = (M + kBM - 1) / kBM, kblocks = (K + kBK - 1) / kBK;
-    tile_major_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(W, c->Wt + off, M, K, tiles_m, kblocks);
+    l2b_tile_major_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(W, c->Wt + off, M, K, tiles_m, kblocks);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(c, L2B_ECUDA, "tile_major_kernel: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(c, L2B_ECUDA, "l2b_tile_major_kernel: %s", cudaGetErrorString(e));
     return 0;
   };
   int rc = 0;
@@ -522,8 +511,8 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
     while (C > 1 && (D / C < 512 || C * B > 512)) C >>= 1;
     if (B >= 128) C = 1;
     if (C == 1)
-      return launch(c, L2B_K_BATCH_EPI, (const void*)bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
-    return launch(c, L2B_K_BATCH_EPI, (const void*)bat_resid_rms_cluster_kernel, dim3(C, B), dim3(256), 0, C, args,
+      return launch(c, L2B_K_BATCH_EPI, (const void*)l2b_bat_resid_rms_kernel, dim3(B), dim3(256), 0, 1, args, st);
+    return launch(c, L2B_K_BATCH_EPI, (const void*)l2b_bat_resid_rms_cluster_kernel, dim3(C, B), dim3(256), 0, C, args,
                   st);
   };
 
@@ -541,7 +530,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
       q.kc = c->kc + (size_t)l * kv_layer + v.kv_off; q.vc = c->vc + (size_t)l * kv_layer + v.kv_off;
       q.kv_seq_stride = v.kv_stride;
       void* args[] = {&q};
-      rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_qkv_epi_kernel, dim3((3 * D / 4 + 255) / 256, B), dim3(256), 0,
+      rc = launch(c, L2B_K_BATCH_EPI, (const void*)l2b_bat_qkv_epi_kernel, dim3((3 * D / 4 + 255) / 256, B), dim3(256), 0,
                   1, args, st);
       if (rc) return rc;
     }
@@ -566,11 +555,11 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
         a.sc_cap = (c->steps + 3) & ~3;
         a.nbatch = B;
         const int wpc = kAttnWarpThreads / 32;
-        rc = launch(c, L2B_K_ATTN, (const void*)attn_warp_kernel, dim3((B * H + wpc - 1) / wpc),
+        rc = launch(c, L2B_K_ATTN, (const void*)l2b_attn_warp_kernel, dim3((B * H + wpc - 1) / wpc),
                     dim3(kAttnWarpThreads), (size_t)wpc * a.sc_cap * 4, 1, args, st);
       } else {
         const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
-        rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B), dim3(kAttnThreads), smem, cs,
+        rc = launch(c, L2B_K_ATTN, (const void*)l2b_attn_decode_kernel, dim3(cs, H, B), dim3(kAttnThreads), smem, cs,
                     args, st);
       }
       if (rc) return rc;
@@ -586,7 +575,7 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
       memset(&w, 0, sizeof w);
       w.P = c->P; w.S = S; w.B = B; w.F = F; w.xh = c->XhF; w.xl = c->XlF; w.npad = c->Bpad;
       void* args[] = {&w};
-      rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_swiglu_kernel, dim3((F / 4 + 255) / 256, B), dim3(256), 0, 1, args,
+      rc = launch(c, L2B_K_BATCH_EPI, (const void*)l2b_bat_swiglu_kernel, dim3((F / 4 + 255) / 256, B), dim3(256), 0, 1, args,
                   st);
       if (rc) return rc;
     }
@@ -621,11 +610,11 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
     g.P = c->P; g.S = S; g.B = B; g.V = V; g.logits = c->logits; g.ctl = v.ctl;
     g.next = c->d_dev + 1; g.forced = c->d_forced; g.out_tokens = c->d_out;
     void* args[] = {&g};
-    rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_logits_kernel, dim3(B), dim3(1024), 0, 1, args, st);
+    rc = launch(c, L2B_K_BATCH_EPI, (const void*)l2b_bat_logits_kernel, dim3(B), dim3(1024), 0, 1, args, st);
     if (rc) return rc;
     int* ctl = v.ctl;
     void* args2[] = {&ctl};
-    rc = launch(c, L2B_K_BATCH_EPI, (const void*)bat_step_kernel, dim3(1), dim3(32), 0, 1, args2, st);
+    rc = launch(c, L2B_K_BATCH_EPI, (const void*)l2b_bat_step_kernel, dim3(1), dim3(32), 0, 1, args2, st);
     if (rc) return rc;
   }
   return 0;
@@ -723,7 +712,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       for (int g = 0; g < G; ++g) f.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
       const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
       void* args[] = {&f};
-      int rc = launch(c, L2B_K_QKV, (const void*)qkv_attn_tp_kernel, dim3(fcs, Hl, 1), dim3(kFThreads), smem, fcs,
+      int rc = launch(c, L2B_K_QKV, (const void*)l2b_qkv_attn_tp_kernel, dim3(fcs, Hl, 1), dim3(kFThreads), smem, fcs,
                       args, st);
       if (rc) return rc;
     } else {
@@ -767,7 +756,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       for (int g = 0; g < G; ++g) a.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
       const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
-      int rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, Hl, 1), dim3(kAttnThreads), smem,
+      int rc = launch(c, L2B_K_ATTN, (const void*)l2b_attn_decode_kernel, dim3(cs, Hl, 1), dim3(kAttnThreads), smem,
                       cs, args, st);
       if (rc) return rc;
     }
@@ -841,7 +830,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
     f.out_tokens = c->d_out;
     f.err = c->tp_err;
     void* args[] = {&f};
-    int rc = launch(c, L2B_K_CLS, (const void*)tp_finalize_kernel, dim3(1), dim3(32), 0, 1, args, st);
+    int rc = launch(c, L2B_K_CLS, (const void*)l2b_tp_finalize_kernel, dim3(1), dim3(32), 0, 1, args, st);
     if (rc) return rc;
   }
   return 0;
@@ -940,7 +929,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       }
       const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
       void* args[] = {&f};
-      int rc = launch(c, L2B_K_QKV, (const void*)qkv_attn_kernel, dim3(fcs, H, 1), dim3(kFThreads), smem, fcs, args,
+      int rc = launch(c, L2B_K_QKV, (const void*)l2b_qkv_attn_kernel, dim3(fcs, H, 1), dim3(kFThreads), smem, fcs, args,
                       st);
       if (rc) return rc;
     } else {
@@ -984,7 +973,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       }
       const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
-      int rc = launch(c, L2B_K_ATTN, (const void*)attn_decode_kernel, dim3(cs, H, B),
+      int rc = launch(c, L2B_K_ATTN, (const void*)l2b_attn_decode_kernel, dim3(cs, H, B),
                       dim3(kAttnThreads), smem, cs, args, st);
       if (rc) return rc;
     }
@@ -1041,6 +1030,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   return 0;
 }
 
+#ifdef L2B_EXPERIMENTS
 // Batch-1 persistent kernel: one cooperative launch runs n_steps decode steps.
 int launch_mega(l2b_ctx* c, int n_steps, cudaStream_t st) {
   MegaParams m;
@@ -1195,14 +1185,76 @@ int launch_stream(l2b_ctx* c, int n_steps, cudaStream_t st) {
   return 0;
 }
 
-// Runs `n_steps` decode steps for B sequences, graph-launched when enabled.
-// Events ev0/ev1 bracket the device work on the ctx stream.
-int run_steps(l2b_ctx* c, int B, int n_steps) {
-  const int64_t l0 = c->launch_counter;
+#endif  // L2B_EXPERIMENTS
+
+// A step sequence is issued in two phases so that ONE host thread can drive several devices
+// whose kernels wait for each other (single-process tensor parallel): begin_steps() does
+// everything that may synchronise or capture (tile-major weights, graph instantiation),
+// issue_steps() only enqueues.
+struct StepPlan {
+  cudaGraphExec_t ge = nullptr;   // nullptr: launch kernel by kernel
+  int per_step = 0;               // kernel launches per step
+};
+
+int begin_steps(l2b_ctx* c, int B, StepPlan* plan) {
+  c->last_tc = false;
   if (c->tp_size == 1 && c->opt.tc_min_batch > 0 && B >= c->opt.tc_min_batch && c->P != nullptr) {
     int rc = ensure_tc_weights(c);  // tile-major weight copy of the tensor-core path
     if (rc) return rc;
+    c->last_tc = true;
   }
+  plan->ge = nullptr;
+  plan->per_step = 0;
+  const bool use_graph = c->opt.graph != 0 && !c->profiling;
+  if (!use_graph) return 0;
+  auto it = c->graphs.find(B);
+  if (it == c->graphs.end()) {
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    const int64_t before = c->launch_counter;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return fail(c, L2B_ECUDA, "begin capture: %s", cudaGetErrorString(e));
+    int rc = enqueue_step(c, B, c->stream);
+    e = cudaStreamEndCapture(c->stream, &g);
+    const int per_step = (int)(c->launch_counter - before);
+    c->launch_counter = before;
+    if (rc) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(c, L2B_ECUDA, "end capture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(c, L2B_ECUDA, "graph instantiate: %s", cudaGetErrorString(e));
+    c->graphs[B] = ge;
+    c->graph_launches[B] = per_step;
+    it = c->graphs.find(B);
+  }
+  plan->ge = it->second;
+  plan->per_step = c->graph_launches[B];
+  return 0;
+}
+
+int issue_steps(l2b_ctx* c, int B, const StepPlan& plan, int count) {
+  if (plan.ge) {
+    for (int s = 0; s < count; ++s) CU(c, cudaGraphLaunch(plan.ge, c->stream));
+    c->launch_counter += (int64_t)count * plan.per_step;
+    return 0;
+  }
+  for (int s = 0; s < count; ++s) {
+    int rc = enqueue_step(c, B, c->stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// Runs `n_steps` decode steps for B sequences on ONE context, graph-launched when enabled.
+// Events ev0/ev1 bracket the device work on the ctx stream.
+int run_steps(l2b_ctx* c, int B, int n_steps) {
+  const int64_t l0 = c->launch_counter;
+#ifdef L2B_EXPERIMENTS
+  c->last_tc = false;
   if (use_mega(c, B)) {
     CU(c, cudaEventRecord(c->ev0, c->stream));
     int rc = launch_mega(c, n_steps, c->stream);
@@ -1219,53 +1271,94 @@ int run_steps(l2b_ctx* c, int B, int n_steps) {
     c->last_launches = c->launch_counter - l0;
     return 0;
   }
-  const bool use_graph = c->opt.graph != 0 && !c->profiling;
-  cudaGraphExec_t ge = nullptr;
-  if (use_graph) {
-    auto it = c->graphs.find(B);
-    if (it == c->graphs.end()) {
-      cudaGraph_t g = nullptr;
-      const int64_t before = c->launch_counter;
-      cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-      if (e != cudaSuccess) return fail(c, L2B_ECUDA, "begin capture: %s", cudaGetErrorString(e));
-      int rc = enqueue_step(c, B, c->stream);
-      e = cudaStreamEndCapture(c->stream, &g);
-      const int per_step = (int)(c->launch_counter - before);
-      c->launch_counter = before;
-      if (rc) {
-        if (g) cudaGraphDestroy(g);
-        cudaGetLastError();
-        return rc;
-      }
-      if (e != cudaSuccess) return fail(c, L2B_ECUDA, "end capture: %s", cudaGetErrorString(e));
-      e = cudaGraphInstantiate(&ge, g, 0);
-      cudaGraphDestroy(g);
-      if (e != cudaSuccess) return fail(c, L2B_ECUDA, "graph instantiate: %s", cudaGetErrorString(e));
-      c->graphs[B] = ge;
-      c->graph_launches[B] = per_step;
-    } else {
-      ge = it->second;
-    }
-  }
+#endif
+  StepPlan plan;
+  int rc = begin_steps(c, B, &plan);
+  if (rc) return rc;
   CU(c, cudaEventRecord(c->ev0, c->stream));
-  if (use_graph) {
-    for (int s = 0; s < n_steps; ++s) CU(c, cudaGraphLaunch(ge, c->stream));
-    c->launch_counter += (int64_t)n_steps * c->graph_launches[B];
-  } else {
-    for (int s = 0; s < n_steps; ++s) {
-      int rc = enqueue_step(c, B, c->stream);
-      if (rc) return rc;
-    }
-  }
+  rc = issue_steps(c, B, plan, n_steps);
+  if (rc) return rc;
   CU(c, cudaEventRecord(c->ev1, c->stream));
   c->last_launches = c->launch_counter - l0;
+  return 0;
+}
+
+// ---- context groups ------------------------------------------------------------------------
+// Every step-type entry point works on "parts": (member context, first global sequence, count).
+// A plain context is a group of one.  All members are driven from the calling thread: inputs are
+// staged everywhere, then the steps are enqueued round-robin (a tensor-parallel rank's kernels
+// spin on data its peers produce, so no member may be synchronised before every member has its
+// work), then results are copied out and the streams are synchronised.
+struct Part {
+  l2b_ctx* k;
+  int b0, nb;
+};
+
+bool is_group(const l2b_ctx* c) { return !c->kids.empty(); }
+bool is_tp_group(const l2b_ctx* c) { return !c->kids.empty() && c->kids[0]->tp_size > 1; }
+
+void parts_of(l2b_ctx* c, int B, std::vector<Part>* out) {
+  out->clear();
+  if (!is_group(c)) {
+    out->push_back({c, 0, B});
+  } else if (is_tp_group(c)) {
+    for (l2b_ctx* k : c->kids) out->push_back({k, 0, B});   // every rank sees the same token
+  } else {
+    for (size_t g = 0; g < c->kids.size(); ++g) {
+      const int b0 = (int)g * c->per_kid;
+      if (b0 >= B) break;
+      out->push_back({c->kids[g], b0, (B - b0) < c->per_kid ? (B - b0) : c->per_kid});
+    }
+  }
+}
+
+// error of a member -> the group handle the caller holds
+int lift(l2b_ctx* c, const l2b_ctx* k, int rc) {
+  if (rc && k != c) c->err = k->err;
+  return rc;
+}
+
+int run_parts(l2b_ctx* c, const std::vector<Part>& parts, int n_steps) {
+  if (parts.size() == 1) {
+    cudaSetDevice(parts[0].k->device);
+    return lift(c, parts[0].k, run_steps(parts[0].k, parts[0].nb, n_steps));
+  }
+  std::vector<StepPlan> plans(parts.size());
+  std::vector<int64_t> l0(parts.size());
+  for (size_t i = 0; i < parts.size(); ++i) {
+    l2b_ctx* k = parts[i].k;
+    CU(c, cudaSetDevice(k->device));
+    l0[i] = k->launch_counter;
+    int rc = begin_steps(k, parts[i].nb, &plans[i]);
+    if (rc) return lift(c, k, rc);
+  }
+  for (size_t i = 0; i < parts.size(); ++i) {
+    CU(c, cudaSetDevice(parts[i].k->device));
+    CU(c, cudaEventRecord(parts[i].k->ev0, parts[i].k->stream));
+  }
+  for (int s = 0; s < n_steps; ++s)
+    for (size_t i = 0; i < parts.size(); ++i) {
+      CU(c, cudaSetDevice(parts[i].k->device));
+      int rc = issue_steps(parts[i].k, parts[i].nb, plans[i], 1);
+      if (rc) return lift(c, parts[i].k, rc);
+    }
+  for (size_t i = 0; i < parts.size(); ++i) {
+    l2b_ctx* k = parts[i].k;
+    CU(c, cudaSetDevice(k->device));
+    CU(c, cudaEventRecord(k->ev1, k->stream));
+    k->last_launches = k->launch_counter - l0[i];
+  }
   return 0;
 }
 
 int finish(l2b_ctx* c) {
   if (c->tp_size > 1)
     CU(c, cudaMemcpyAsync(c->h_err, c->tp_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+#ifdef L2B_EXPERIMENTS
   const bool ll = c->ll_used && c->tp_size == 1;
+#else
+  const bool ll = false;
+#endif
   if (ll) {
     int* derr = reinterpret_cast<int*>(c->d_ll + 3 * (size_t)c->D);
     CU(c, cudaMemcpyAsync(c->h_err, derr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1289,10 +1382,42 @@ int finish(l2b_ctx* c) {
 
 int check_ready(l2b_ctx* c) {
   if (!c) return L2B_EINVAL;
+  if (is_group(c)) {
+    for (l2b_ctx* k : c->kids) {
+      int rc = check_ready(k);
+      if (rc) return lift(c, k, rc);
+    }
+    return 0;
+  }
   if (!l2b_weights_ready(c)) return fail(c, L2B_ESTATE, "weights not fully uploaded");
   if (c->tp_size > 1 && !c->tp_connected)
     return fail(c, L2B_ESTATE, "tensor-parallel context not connected (l2b_tp_export / l2b_tp_connect)");
   return 0;
+}
+
+// B sequences of a call against the capacity of the context (group: the global batch)
+int check_batch(l2b_ctx* c, int B) {
+  const int cap = is_tp_group(c) ? 1 : c->Bmax;
+  if (B < 1 || B > cap) return fail(c, L2B_EINVAL, "B=%d outside [1,%d]", B, cap);
+  return 0;
+}
+
+int finish_parts(l2b_ctx* c, const std::vector<Part>& parts) {
+  int first = 0;
+  for (const Part& p : parts) {   // synchronise every member even after a failure
+    cudaSetDevice(p.k->device);
+    int rc = finish(p.k);
+    if (rc && !first) first = lift(c, p.k, rc);
+  }
+  if (is_group(c)) {
+    c->last_ms = 0.f;
+    c->last_launches = 0;
+    for (const Part& p : parts) {
+      if (p.k->last_ms > c->last_ms) c->last_ms = p.k->last_ms;   // the slowest member
+      c->last_launches += p.k->last_launches;
+    }
+  }
+  return first;
 }
 
 // Validates (token,pos) of sequence b and fills the pinned header.
@@ -1303,7 +1428,7 @@ int stage_inputs(l2b_ctx* c, int B, const int32_t* tokens, const int32_t* pos, i
   for (int b = 0; b < B; ++b) {
     if (tokens[b] < 0 || tokens[b] >= c->V)
       return fail(c, L2B_EINVAL, "token %d of sequence %d outside [0,%d)", tokens[b], b, c->V);
-    if (pos[b] < 0 || pos[b] + n_steps > c->steps)
+    if (pos[b] < 0 || n_steps > c->steps || pos[b] > c->steps - n_steps)
       return fail(c, L2B_EINVAL, "pos %d (+%d steps) of sequence %d outside the %d cached rows",
                   pos[b], n_steps, b, c->steps);
     if (pos[b] > c->n_run[b])
@@ -1441,7 +1566,7 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     TRY(dev_alloc(c, &tpw, 8, true));
     c->tp_epoch = tpw;
     c->tp_ticket = tpw ? tpw + 1 : nullptr;
-    c->tp_err = tpw ? tpw + 2 : nullptr;
+    c->tp_err = tpw ? tpw + 2 : nullptr;   // tpw[3]: time-out in units of 2^20 clocks, written below
   }
   TRY(dev_alloc(c, &c->q, sB * sDl, true));
   const size_t kv = sL * sB * sDl * (size_t)max_steps;
@@ -1482,6 +1607,7 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev1);
     if (e2 != cudaSuccess) rc = fail(c, L2B_ECUDA, "host/stream setup: %s", cudaGetErrorString(e2));
   }
+  if (!rc) rc = write_tp_timeout(c);
   if (!rc) {
     // the zero-fills above ran on the NULL stream; the ctx stream is non-blocking
     cudaError_t e3 = cudaDeviceSynchronize();
@@ -1506,15 +1632,92 @@ L2B_API int l2b_create_tp(const int32_t hdr[7], int32_t device, int32_t max_step
   return create_common(hdr, device, 1, max_steps, tp_rank, tp_size, out);
 }
 
+// Single-process multi-GPU context ("l2b_create(hdr, n_gpus, tp_degree, max_batch,
+// max_steps)"): one host thread -- the reference is one JS thread, llama2.ts:468 -- drives devices
+// 0..n_gpus-1.  tp_degree == 1: the batch is partitioned over the GPUs (weights replicated, no
+// collective).  tp_degree == n_gpus: ONE tensor-parallel group decoding one sequence; the ranks'
+// exchange blocks are mapped into each other with cudaDeviceEnablePeerAccess (no IPC handles).
+L2B_API int l2b_create_multi(const int32_t hdr[7], int32_t n_gpus, int32_t tp_degree, int32_t max_batch,
+                             int32_t max_steps, l2b_ctx** out) {
+  if (!hdr || !out) return fail(nullptr, L2B_EINVAL, "null hdr/out");
+  *out = nullptr;
+  if (n_gpus < 1 || n_gpus > kMaxTp) return fail(nullptr, L2B_EINVAL, "n_gpus %d outside [1,%d]", n_gpus, kMaxTp);
+  if (tp_degree != 1 && tp_degree != n_gpus)
+    return fail(nullptr, L2B_EINVAL, "tp_degree must be 1 (batch partition) or n_gpus (one tensor-parallel group)");
+  if (max_batch < 1) return fail(nullptr, L2B_EINVAL, "max_batch must be >= 1");
+  const bool tp = tp_degree > 1;
+  if (tp && max_batch != 1) return fail(nullptr, L2B_EINVAL, "a tensor-parallel group decodes one sequence (max_batch 1)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, L2B_ECUDA, "no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (n_gpus > ndev) return fail(nullptr, L2B_EINVAL, "n_gpus %d but only %d device(s) visible", n_gpus, ndev);
+
+  l2b_ctx* g = new l2b_ctx();
+  g->per_kid = (max_batch + n_gpus - 1) / n_gpus;
+  int rc = 0;
+  for (int r = 0; r < n_gpus && !rc; ++r) {
+    l2b_ctx* k = nullptr;
+    rc = tp ? create_common(hdr, r, 1, max_steps, r, n_gpus, &k) : create_common(hdr, r, g->per_kid, max_steps, 0, 1, &k);
+    if (!rc) g->kids.push_back(k);
+  }
+  if (!rc && tp && n_gpus > 1) {
+    for (int a = 0; a < n_gpus && !rc; ++a) {
+      cudaSetDevice(a);
+      for (int b = 0; b < n_gpus && !rc; ++b) {
+        if (a == b) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, a, b);
+        if (!can) { rc = fail(nullptr, L2B_ECOMM, "device %d cannot map device %d's memory (no NVLink/P2P)", a, b); break; }
+        e = cudaDeviceEnablePeerAccess(b, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          rc = fail(nullptr, L2B_ECOMM, "cudaDeviceEnablePeerAccess(%d -> %d): %s", a, b, cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    }
+    if (!rc)
+      for (l2b_ctx* k : g->kids) {
+        for (int r = 0; r < n_gpus; ++r) k->peer[r] = g->kids[r]->xchg;
+        k->tp_connected = true;
+      }
+  }
+  if (rc) {
+    const std::string msg = g_create_error;
+    l2b_destroy(g);
+    g_create_error = msg;
+    return rc;
+  }
+  l2b_ctx* k0 = g->kids[0];
+  g->D = k0->D; g->F = k0->F; g->L = k0->L; g->H = k0->H; g->hs = k0->hs; g->V = k0->V; g->S = k0->S;
+  g->shared_cls = k0->shared_cls;
+  g->device = 0;
+  g->steps = k0->steps;
+  g->Bmax = tp ? 1 : max_batch;
+  *out = g;
+  return L2B_OK;
+}
+
 L2B_API void l2b_destroy(l2b_ctx* c) {
   if (!c) return;
+  if (!c->kids.empty()) {
+    for (l2b_ctx* k : c->kids) {   // nobody may still be spinning on a peer that is being freed
+      cudaSetDevice(k->device);
+      if (k->stream) cudaStreamSynchronize(k->stream);
+    }
+    for (l2b_ctx* k : c->kids) l2b_destroy(k);
+    delete c;
+    return;
+  }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   drop_graphs(c);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   if (c->tp_size > 1) {
     for (int g = 0; g < c->tp_size; ++g)
-      if (g != c->tp_rank && c->peer[g]) cudaIpcCloseMemHandle(c->peer[g]);
+      if (g != c->tp_rank && c->peer[g] && c->peer_ipc) cudaIpcCloseMemHandle(c->peer[g]);
     if (c->xchg) cudaFree(c->xchg);
     if (c->tp_epoch) cudaFree(c->tp_epoch);
     c->x = c->xb = c->hb = c->logits = nullptr;
@@ -1529,7 +1732,7 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
   for (float* p : fl)
     if (p) cudaFree(p);
   int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->d_work, c->d_sync, c->samp_i, (int*)c->samp_f,
-               (int*)c->d_ll};
+               (int*)c->d_ll, (int*)c->d_dbg, (int*)c->d_dbg2};
   for (int* p : il)
     if (p) cudaFree(p);
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -1599,6 +1802,13 @@ L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float
                        uint64_t n_floats) {
   if (!c) return L2B_EINVAL;
   if (!host) return fail(c, L2B_EINVAL, "null host pointer");
+  if (is_group(c)) {   // replicas keep the whole tensor, tensor-parallel ranks their rows
+    for (l2b_ctx* k : c->kids) {
+      int rc = l2b_upload(k, tensor_id, layer, host, n_floats);
+      if (rc) return lift(c, k, rc);
+    }
+    return L2B_OK;
+  }
   Placement pl;
   int rc = placement(c, tensor_id, layer, &pl);
   if (rc) return rc;
@@ -1606,8 +1816,7 @@ L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float
     return fail(c, L2B_EINVAL, "tensor %d expects %zu floats, got %llu", tensor_id, pl.expect,
                 (unsigned long long)n_floats);
   CU(c, cudaSetDevice(c->device));
-  // make sure no step is still reading the old contents
-  CU(c, cudaStreamSynchronize(c->stream));
+  // stream-ordered behind any step still reading the old contents
   CU(c, cudaMemcpy2DAsync(pl.dst, pl.dst_pitch * sizeof(float), host + pl.src_off, pl.row * sizeof(float),
                           pl.row * sizeof(float), pl.rows, cudaMemcpyDefault, c->stream));
   // the copy runs on the ctx stream (device sources are asynchronous otherwise): the
@@ -1625,6 +1834,15 @@ L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float
 // q/k/v stacking).  Shard-aware: a tensor-parallel rank preads only its own rows.
 L2B_API int l2b_load_checkpoint(l2b_ctx* c, const char* path, double* seconds_out) {
   if (!c || !path) return L2B_EINVAL;
+  if (is_group(c)) {   // every member streams the file (tensor-parallel ranks: only their rows)
+    const auto g0 = std::chrono::steady_clock::now();
+    for (l2b_ctx* k : c->kids) {
+      int rc = l2b_load_checkpoint(k, path, nullptr);
+      if (rc) return lift(c, k, rc);
+    }
+    if (seconds_out) *seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - g0).count();
+    return L2B_OK;
+  }
   CU(c, cudaSetDevice(c->device));
   const int fd = open(path, O_RDONLY);
   if (fd < 0) return fail(c, L2B_EINVAL, "cannot open %s", path);
@@ -1641,16 +1859,28 @@ L2B_API int l2b_load_checkpoint(l2b_ctx* c, const char* path, double* seconds_ou
   }
   const size_t kChunk = (size_t)32 << 20;
   unsigned char* stage[2] = {nullptr, nullptr};
-  cudaEvent_t ev[2];
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  auto cleanup = [&]() {   // every exit below goes through here
+    for (int i = 0; i < 2; ++i) {
+      if (stage[i]) cudaFreeHost(stage[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    close(fd);
+  };
   cudaError_t e = cudaMallocHost((void**)&stage[0], kChunk);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&stage[1], kChunk);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
   if (e != cudaSuccess) {
-    close(fd);
+    cudaGetLastError();
+    cleanup();
     return fail(c, L2B_ENOMEM, "pinned staging: %s", cudaGetErrorString(e));
   }
-  CU(c, cudaStreamSynchronize(c->stream));
+  e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(c, L2B_ECUDA, "stream sync: %s", cudaGetErrorString(e));
+  }
   const auto t0 = std::chrono::steady_clock::now();
   // file order (llama2.ts:114-127)
   static const int order[] = {L2B_T_TOKEN_EMBEDDING_TABLE, L2B_T_RMS_ATT_WEIGHT, L2B_T_WQ, L2B_T_WK, L2B_T_WV,
@@ -1696,16 +1926,17 @@ L2B_API int l2b_load_checkpoint(l2b_ctx* c, const char* path, double* seconds_ou
   cudaStreamSynchronize(c->stream);
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (seconds_out) *seconds_out = secs;
-  cudaFreeHost(stage[0]);
-  cudaFreeHost(stage[1]);
-  cudaEventDestroy(ev[0]);
-  cudaEventDestroy(ev[1]);
-  close(fd);
+  cleanup();
   return rc;
 }
 
 L2B_API int l2b_weights_ready(const l2b_ctx* c) {
   if (!c) return 0;
+  if (!c->kids.empty()) {
+    for (const l2b_ctx* k : c->kids)
+      if (!l2b_weights_ready(k)) return 0;
+    return 1;
+  }
   for (int t = 0; t < L2B_T_COUNT; ++t) {
     const bool layered = (t >= L2B_T_RMS_ATT_WEIGHT && t <= L2B_T_W3);
     if (t == L2B_T_WCLS && c->shared_cls) continue;
@@ -1720,21 +1951,35 @@ L2B_API int l2b_forward_batch(l2b_ctx* c, int32_t B, const int32_t* tokens, cons
                               float* logits_out, int32_t* argmax_out) {
   int rc = check_ready(c);
   if (rc) return rc;
-  CU(c, cudaSetDevice(c->device));
-  rc = stage_inputs(c, B, tokens, pos, 0, 0, 0, 1);
+  if ((rc = check_batch(c, B))) return rc;
+  if (!tokens || !pos) return fail(c, L2B_EINVAL, "null tokens/pos");
+  std::vector<Part> parts;
+  parts_of(c, B, &parts);
+  for (const Part& p : parts) {
+    CU(c, cudaSetDevice(p.k->device));
+    rc = stage_inputs(p.k, p.nb, tokens + p.b0, pos + p.b0, 0, 0, 0, 1);
+    if (rc) return lift(c, p.k, rc);
+  }
+  rc = run_parts(c, parts, 1);
   if (rc) return rc;
-  rc = run_steps(c, B, 1);
+  const size_t n_out = is_tp_group(c) ? 1 : parts.size();   // every rank of a tp group holds the result
+  for (size_t i = 0; i < n_out; ++i) {
+    l2b_ctx* k = parts[i].k;
+    CU(c, cudaSetDevice(k->device));
+    if (logits_out)
+      CU(c, cudaMemcpyAsync(k->h_logits, k->logits, sizeof(float) * (size_t)parts[i].nb * k->V,
+                            cudaMemcpyDeviceToHost, k->stream));
+    if (argmax_out)
+      CU(c, cudaMemcpyAsync(k->h_out, k->d_dev + 1, sizeof(int) * parts[i].nb, cudaMemcpyDeviceToHost, k->stream));
+  }
+  rc = finish_parts(c, parts);
   if (rc) return rc;
-  if (logits_out)
-    CU(c, cudaMemcpyAsync(c->h_logits, c->logits, sizeof(float) * (size_t)B * c->V,
-                          cudaMemcpyDeviceToHost, c->stream));
-  if (argmax_out)
-    CU(c, cudaMemcpyAsync(c->h_out, c->d_dev + 1, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
-  rc = finish(c);
-  if (rc) return rc;
-  if (logits_out) memcpy(logits_out, c->h_logits, sizeof(float) * (size_t)B * c->V);
-  if (argmax_out) memcpy(argmax_out, c->h_out, sizeof(int) * B);
-  mark_run(c, B, pos, 1);
+  for (size_t i = 0; i < n_out; ++i) {
+    const Part& p = parts[i];
+    if (logits_out) memcpy(logits_out + (size_t)p.b0 * c->V, p.k->h_logits, sizeof(float) * (size_t)p.nb * c->V);
+    if (argmax_out) memcpy(argmax_out + p.b0, p.k->h_out, sizeof(int) * p.nb);
+  }
+  for (const Part& p : parts) mark_run(p.k, p.nb, pos + p.b0, 1);
   return L2B_OK;
 }
 
@@ -1792,10 +2037,18 @@ L2B_API int l2b_prefill(l2b_ctx* c, int32_t seq, int32_t n_tokens, const int32_t
                         float* logits_out, int32_t* argmax_out) {
   int rc = check_ready(c);
   if (rc) return rc;
-  if (c->tp_size > 1) return fail(c, L2B_ESTATE, "prefill is not available on a tensor-parallel context");
+  if (c->tp_size > 1 || is_tp_group(c))
+    return fail(c, L2B_ESTATE, "prefill is not available on a tensor-parallel context");
   if (seq < 0 || seq >= c->Bmax) return fail(c, L2B_EINVAL, "seq %d outside [0,%d)", seq, c->Bmax);
+  if (is_group(c)) {   // the member that owns this sequence
+    l2b_ctx* k = c->kids[seq / c->per_kid];
+    rc = lift(c, k, l2b_prefill(k, seq % c->per_kid, n_tokens, tokens, pos0, logits_out, argmax_out));
+    c->last_ms = k->last_ms;
+    c->last_launches = k->last_launches;
+    return rc;
+  }
   if (n_tokens < 1 || !tokens) return fail(c, L2B_EINVAL, "n_tokens < 1 or null tokens");
-  if (pos0 < 0 || pos0 + n_tokens > c->steps)
+  if (pos0 < 0 || n_tokens > c->steps || pos0 > c->steps - n_tokens)
     return fail(c, L2B_EINVAL, "positions %d..%d outside the %d cached rows", pos0, pos0 + n_tokens - 1, c->steps);
   if (pos0 > c->n_run[seq])
     return fail(c, L2B_EORDER, "pos %d of sequence %d called before positions %d..%d were run", pos0, seq,
@@ -1808,6 +2061,7 @@ L2B_API int l2b_prefill(l2b_ctx* c, int32_t seq, int32_t n_tokens, const int32_t
   if (rc) return rc;
   rc = ensure_tc_weights(c);
   if (rc) return rc;
+  c->last_tc = true;
   const size_t kv_seq = (size_t)c->H * c->steps * c->hs;
   const int64_t l0 = c->launch_counter;
   CU(c, cudaEventRecord(c->ev0, c->stream));
@@ -1853,7 +2107,7 @@ static int enqueue_sampler(l2b_ctx* c, const float* logits, double temperature, 
   sp.cand_i = c->samp_i; sp.sort_i = c->samp_i + c->V;
   sp.next = c->d_dev + 1;
   void* args[] = {&sp};
-  return launch(c, L2B_K_CLS, (const void*)sample_kernel, dim3(1), dim3(kSampThreads),
+  return launch(c, L2B_K_CLS, (const void*)l2b_sample_kernel, dim3(1), dim3(kSampThreads),
                 16 * kSampThreads * sizeof(int), 1, args, c->stream);
 }
 
@@ -1863,25 +2117,32 @@ L2B_API int l2b_forward_sample(l2b_ctx* c, int32_t token, int32_t pos, double te
   if (rc) return rc;
   if (!next_out) return fail(c, L2B_EINVAL, "null next_out");
   if (temperature == 0.0) return l2b_forward_argmax(c, token, pos, next_out);  // llama2.ts:476-478
-  CU(c, cudaSetDevice(c->device));
-  rc = stage_inputs(c, 1, &token, &pos, 0, 0, 0, 1);
+  std::vector<Part> parts;
+  parts_of(c, 1, &parts);
+  for (const Part& p : parts) {
+    CU(c, cudaSetDevice(p.k->device));
+    rc = stage_inputs(p.k, 1, &token, &pos, 0, 0, 0, 1);
+    if (rc) return lift(c, p.k, rc);
+  }
+  rc = run_parts(c, parts, 1);
   if (rc) return rc;
-  rc = run_steps(c, 1, 1);
+  l2b_ctx* k = parts[0].k;   // sequence 0 / rank 0 (every tensor-parallel rank holds the full logits)
+  CU(c, cudaSetDevice(k->device));
+  rc = enqueue_sampler(k, k->logits, temperature, topp, (double)rand01);
+  if (rc) return lift(c, k, rc);
+  CU(c, cudaEventRecord(k->ev1, k->stream));
+  CU(c, cudaMemcpyAsync(k->h_out, k->d_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, k->stream));
+  rc = finish_parts(c, parts);
   if (rc) return rc;
-  rc = enqueue_sampler(c, c->logits, temperature, topp, (double)rand01);
-  if (rc) return rc;
-  CU(c, cudaEventRecord(c->ev1, c->stream));
-  CU(c, cudaMemcpyAsync(c->h_out, c->d_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  rc = finish(c);
-  if (rc) return rc;
-  *next_out = c->h_out[0];
-  mark_run(c, 1, &pos, 1);
+  *next_out = k->h_out[0];
+  for (const Part& p : parts) mark_run(p.k, 1, &pos, 1);
   return L2B_OK;
 }
 
 L2B_API int l2b_sample_logits(l2b_ctx* c, const float* logits_host, double temperature, double topp, float rand01,
                               int32_t* next_out) {
   if (!c) return L2B_EINVAL;
+  if (is_group(c)) return lift(c, c->kids[0], l2b_sample_logits(c->kids[0], logits_host, temperature, topp, rand01, next_out));
   if (!logits_host || !next_out) return fail(c, L2B_EINVAL, "null argument");
   if (temperature == 0.0) return fail(c, L2B_EINVAL, "temperature 0 is the argmax path (l2b_forward_argmax)");
   CU(c, cudaSetDevice(c->device));
@@ -1902,25 +2163,50 @@ L2B_API int l2b_generate_greedy(l2b_ctx* c, int32_t B, const int32_t* tokens, co
                                 int32_t n_steps, const int32_t* forced, int32_t* out_tokens) {
   int rc = check_ready(c);
   if (rc) return rc;
+  if ((rc = check_batch(c, B))) return rc;
+  if (!tokens || !pos) return fail(c, L2B_EINVAL, "null tokens/pos");
   if (n_steps < 1 || !out_tokens) return fail(c, L2B_EINVAL, "n_steps < 1 or null out_tokens");
-  CU(c, cudaSetDevice(c->device));
-  rc = stage_inputs(c, B, tokens, pos, 0, forced != nullptr, 1, n_steps);
-  if (rc) return rc;
+  if (n_steps > c->steps) return fail(c, L2B_EINVAL, "n_steps %d > the %d cached rows", n_steps, c->steps);
   const size_t n = (size_t)n_steps * B;
-  if (forced) {
+  if (forced)
     for (size_t i = 0; i < n; ++i)
       if (forced[i] >= c->V) return fail(c, L2B_EINVAL, "forced token %d >= vocab", forced[i]);
-    memcpy(c->h_out, forced, sizeof(int) * n);
-    CU(c, cudaMemcpyAsync(c->d_forced, c->h_out, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));  // h_out is reused for the result below
+  std::vector<Part> parts;
+  parts_of(c, B, &parts);
+  for (const Part& p : parts) {
+    l2b_ctx* k = p.k;
+    CU(c, cudaSetDevice(k->device));
+    rc = stage_inputs(k, p.nb, tokens + p.b0, pos + p.b0, 0, forced != nullptr, 1, n_steps);
+    if (rc) return lift(c, k, rc);
+    if (forced) {   // this member's columns of the [n_steps][B] matrix
+      for (int s = 0; s < n_steps; ++s)
+        memcpy(k->h_out + (size_t)s * p.nb, forced + (size_t)s * B + p.b0, sizeof(int) * p.nb);
+      CU(c, cudaMemcpyAsync(k->d_forced, k->h_out, sizeof(int) * (size_t)n_steps * p.nb, cudaMemcpyHostToDevice,
+                            k->stream));
+    }
   }
-  rc = run_steps(c, B, n_steps);
+  if (forced)   // h_out is reused for the result below
+    for (const Part& p : parts) {
+      CU(c, cudaSetDevice(p.k->device));
+      CU(c, cudaStreamSynchronize(p.k->stream));
+    }
+  rc = run_parts(c, parts, n_steps);
   if (rc) return rc;
-  CU(c, cudaMemcpyAsync(c->h_out, c->d_out, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
-  rc = finish(c);
+  const size_t n_out = is_tp_group(c) ? 1 : parts.size();
+  for (size_t i = 0; i < n_out; ++i) {
+    l2b_ctx* k = parts[i].k;
+    CU(c, cudaSetDevice(k->device));
+    CU(c, cudaMemcpyAsync(k->h_out, k->d_out, sizeof(int) * (size_t)n_steps * parts[i].nb, cudaMemcpyDeviceToHost,
+                          k->stream));
+  }
+  rc = finish_parts(c, parts);
   if (rc) return rc;
-  memcpy(out_tokens, c->h_out, sizeof(int) * n);
-  mark_run(c, B, pos, n_steps);
+  for (size_t i = 0; i < n_out; ++i) {
+    const Part& p = parts[i];
+    for (int s = 0; s < n_steps; ++s)
+      memcpy(out_tokens + (size_t)s * B + p.b0, p.k->h_out + (size_t)s * p.nb, sizeof(int) * p.nb);
+  }
+  for (const Part& p : parts) mark_run(p.k, p.nb, pos + p.b0, n_steps);
   return L2B_OK;
 }
 
@@ -1931,38 +2217,51 @@ L2B_API int l2b_profile_batch(l2b_ctx* c, int32_t B, const int32_t* tokens, cons
                               float* ms_per_class, int32_t* launches_per_class) {
   int rc = check_ready(c);
   if (rc) return rc;
+  if ((rc = check_batch(c, B))) return rc;
+  if (!tokens || !pos) return fail(c, L2B_EINVAL, "null tokens/pos");
   if (!ms_per_class || !launches_per_class) return fail(c, L2B_EINVAL, "null output");
-  CU(c, cudaSetDevice(c->device));
-  rc = stage_inputs(c, B, tokens, pos, 0, 0, 0, 1);
-  if (rc) return rc;
-  c->profiling = true;
-  c->prof_events.clear();
-  c->prof_class.clear();
-  rc = run_steps(c, B, 1);
-  c->profiling = false;
+  std::vector<Part> parts;
+  parts_of(c, B, &parts);
+  for (const Part& p : parts) {
+    CU(c, cudaSetDevice(p.k->device));
+    rc = stage_inputs(p.k, p.nb, tokens + p.b0, pos + p.b0, 0, 0, 0, 1);
+    if (rc) return lift(c, p.k, rc);
+    p.k->profiling = true;
+    p.k->prof_events.clear();
+    p.k->prof_class.clear();
+  }
+  rc = run_parts(c, parts, 1);
+  for (const Part& p : parts) p.k->profiling = false;
   if (!rc) {
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, c->stream);
-    c->prof_events.push_back(e);
-    rc = finish(c);
+    for (const Part& p : parts) {
+      cudaSetDevice(p.k->device);
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, p.k->stream);
+      p.k->prof_events.push_back(e);
+    }
+    rc = finish_parts(c, parts);
   }
   for (int k = 0; k < L2B_K_COUNT; ++k) {
     ms_per_class[k] = 0.f;
     launches_per_class[k] = 0;
   }
   if (!rc) {
-    for (size_t i = 0; i + 1 < c->prof_events.size(); ++i) {
+    l2b_ctx* k0 = parts[0].k;   // the first member's kernels (members run the same launch sequence)
+    cudaSetDevice(k0->device);
+    for (size_t i = 0; i + 1 < k0->prof_events.size(); ++i) {
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]);
-      ms_per_class[c->prof_class[i]] += ms;
-      launches_per_class[c->prof_class[i]] += 1;
+      cudaEventElapsedTime(&ms, k0->prof_events[i], k0->prof_events[i + 1]);
+      ms_per_class[k0->prof_class[i]] += ms;
+      launches_per_class[k0->prof_class[i]] += 1;
     }
-    mark_run(c, B, pos, 1);
+    for (const Part& p : parts) mark_run(p.k, p.nb, pos + p.b0, 1);
   }
-  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
-  c->prof_events.clear();
-  c->prof_class.clear();
+  for (const Part& p : parts) {
+    for (cudaEvent_t e : p.k->prof_events) cudaEventDestroy(e);
+    p.k->prof_events.clear();
+    p.k->prof_class.clear();
+  }
   return rc;
 }
 
@@ -1976,6 +2275,10 @@ L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer
   if (!c) return L2B_EINVAL;
   if (!out) return fail(c, L2B_EINVAL, "null out");
   if (seq < 0 || seq >= c->Bmax) return fail(c, L2B_EINVAL, "seq %d", seq);
+  if (is_group(c)) {
+    l2b_ctx* k = is_tp_group(c) ? c->kids[0] : c->kids[seq / c->per_kid];
+    return lift(c, k, l2b_read_state(k, which, is_tp_group(c) ? 0 : seq % c->per_kid, layer, pos, out, n_floats));
+  }
   if (c->tp_size > 1 && which != L2B_S_LOGITS)
     return fail(c, L2B_ESTATE, "only the logits tap exists in tensor-parallel mode (state is sharded / LL-tagged)");
   CU(c, cudaSetDevice(c->device));
@@ -1987,7 +2290,11 @@ L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer
     case L2B_S_X: src = c->x + seq * D; break;
     case L2B_S_Q: src = c->q + seq * D; break;
     case L2B_S_XB: src = c->xb + seq * D; break;
-    case L2B_S_HB: src = c->hb + (size_t)seq * c->F; n = c->F; break;
+    case L2B_S_HB:
+      if (c->last_tc)
+        return fail(c, L2B_ESTATE, "hb is not materialised on the tensor-core path (the SwiGLU output exists only "
+                                   "as the pre-split operand of the w2 GEMM)");
+      src = c->hb + (size_t)seq * c->F; n = c->F; break;
     case L2B_S_LOGITS: src = c->logits + (size_t)seq * c->V; n = c->V; break;
     case L2B_S_KEY_ROW:
     case L2B_S_VALUE_ROW: {
@@ -2012,6 +2319,8 @@ L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer
 
 L2B_API int l2b_debug_timeline(l2b_ctx* c, int64_t* out, uint64_t n) {
   if (!c || !out) return L2B_EINVAL;
+  if (is_group(c)) return lift(c, c->kids[0], l2b_debug_timeline(c->kids[0], out, n));
+  CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->stream));
   if (c->d_dbg2 && n == 1024 * 12) {   // GEMV launch timeline
     CU(c, cudaMemcpy(out, c->d_dbg2, n * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -2025,6 +2334,13 @@ L2B_API int l2b_debug_timeline(l2b_ctx* c, int64_t* out, uint64_t n) {
 
 L2B_API int l2b_reset(l2b_ctx* c) {
   if (!c) return L2B_EINVAL;
+  if (is_group(c)) {
+    for (l2b_ctx* k : c->kids) {
+      int rc = l2b_reset(k);
+      if (rc) return lift(c, k, rc);
+    }
+    return L2B_OK;
+  }
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->stream));
   const size_t kv = (size_t)c->L * c->Bmax * c->Dl * (size_t)c->steps;
@@ -2037,6 +2353,13 @@ L2B_API int l2b_reset(l2b_ctx* c) {
 
 L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return L2B_EINVAL;
+  if (is_group(c)) {
+    for (l2b_ctx* k : c->kids) {
+      int rc = l2b_set_option(k, key, value);
+      if (rc) return lift(c, k, rc);
+    }
+    return L2B_OK;
+  }
   Options& o = c->opt;
   const std::string k(key);
   const int v = (int)value;
@@ -2073,11 +2396,21 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
   } else if (k == "fuse_qkv_attn") {
     o.fuse_qkv_attn = v != 0;
   } else if (k == "mega") {
+#ifdef L2B_EXPERIMENTS
     o.mega = v < 0 ? 0 : (v > 2 ? 2 : v);
+#else
+    if (v != 0) return fail(c, L2B_EINVAL, "persistent-kernel experiments are not compiled in (build with -DL2B_EXPERIMENTS)");
+#endif
   } else if (k == "stream_stages") {
     o.stream_stages = v < 0 ? 0 : v;
   } else if (k == "stream_chunks") {
     o.stream_chunks = v < 0 ? 0 : v;
+  } else if (k == "tp_timeout_ms") {
+    if (v < 1) return fail(c, L2B_EINVAL, "tp_timeout_ms must be >= 1");
+    o.tp_timeout_ms = v;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    return write_tp_timeout(c);
   } else if (k == "gemv_timeline") {
     if (v && !c->d_dbg2) {
       if (cudaMalloc((void**)&c->d_dbg2, 1024 * 12 * sizeof(long long)) != cudaSuccess) return fail(c, L2B_ENOMEM, "dbg");
@@ -2110,6 +2443,7 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
 
 L2B_API int64_t l2b_tp_export(l2b_ctx* c, void* blob, uint64_t cap) {
   if (!c) return L2B_EINVAL;
+  if (is_group(c)) return fail(c, L2B_ESTATE, "a single-process group wires its members itself");
   if (c->tp_size <= 1) return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
   if (!blob || cap < sizeof(cudaIpcMemHandle_t)) return fail(c, L2B_EINVAL, "blob needs %zu bytes", sizeof(cudaIpcMemHandle_t));
   CU(c, cudaSetDevice(c->device));
@@ -2121,6 +2455,7 @@ L2B_API int64_t l2b_tp_export(l2b_ctx* c, void* blob, uint64_t cap) {
 
 L2B_API int l2b_tp_connect(l2b_ctx* c, const void* blobs, uint64_t blob_bytes, int32_t n_ranks) {
   if (!c) return L2B_EINVAL;
+  if (is_group(c)) return fail(c, L2B_ESTATE, "a single-process group wires its members itself");
   if (c->tp_size <= 1) return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
   if (!blobs || n_ranks != c->tp_size || blob_bytes < sizeof(cudaIpcMemHandle_t))
     return fail(c, L2B_EINVAL, "expected %d blobs of >= %zu bytes", c->tp_size, sizeof(cudaIpcMemHandle_t));
@@ -2137,6 +2472,7 @@ L2B_API int l2b_tp_connect(l2b_ctx* c, const void* blobs, uint64_t blob_bytes, i
     }
     c->peer[g] = (unsigned char*)p;
   }
+  c->peer_ipc = true;
   c->tp_connected = true;
   drop_graphs(c);
   return L2B_OK;

@@ -95,7 +95,7 @@ __device__ __forceinline__ int block_excl_scan_i32(int v, int* s_warp, int* tota
   return res;
 }
 
-__global__ void __launch_bounds__(kSampThreads) sample_kernel(const __grid_constant__ SampleParams p) {
+__global__ void __launch_bounds__(kSampThreads) l2b_sample_kernel(const __grid_constant__ SampleParams p) {
   __shared__ double s_d[33];
   __shared__ int s_i[33];
   __shared__ float s_f[32];

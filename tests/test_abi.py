@@ -14,7 +14,7 @@ def test_library_builds_and_exports_every_declared_symbol(pkg):
     for n in names:
         assert lib.exported(n), n
         assert n in pkg.capi._SIGNATURES, "capi.py has no prototype for %s" % n
-    assert lib.dll.l2b_abi_version() == 1
+    assert lib.dll.l2b_abi_version() == 2
 
 
 def test_library_is_sm100a_and_has_no_torch_dependency(pkg):
