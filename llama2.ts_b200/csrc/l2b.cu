@@ -369,13 +369,25 @@ int auto_cluster(const l2b_ctx* c, int B) {
 int gemm_n_for(int cols) { return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256; }
 
 // k-split so that (tiles x splits) fills whole waves of the 148 SMs without drowning the
-// step in partial-sum traffic
+// step in partial-sum traffic -- and so that no accumulator sees a chain longer than
+// kMaxChainKb k-blocks: tcgen05.mma adds into TMEM with truncation, the error of a logit grows
+// linearly with the chain (measured on 7B: 1.1e-4 at K = 2752 on ONE accumulator, 1.5e-4 with
+// 256 sequences, where w2 ran as 4 splits of 2752 -- outside the 1e-4 tolerance; chains of
+// <= 1408 stay below 5e-5).  G accumulators rotate inside a work item, so a split may hold
+// G * kMaxChainKb k-blocks.
+constexpr int kMaxChainKb = 44;
+int gemm_rotation(const l2b_ctx* c, int N) {
+  if (c->opt.tc_tmem_a && N <= 128) return N == 32 ? 2 : 1;   // l2b_tc3x_tmemA_matmul_kernel
+  return N == 32 ? 4 : (N == 64 ? 2 : 1);                      // l2b_tc3x_matmul_kernel
+}
 int pick_splits(const l2b_ctx* c, int M, int K, int B) {
   if (c->opt.tc_splits > 0) return c->opt.tc_splits < c->Smax ? c->opt.tc_splits : c->Smax;
   const int tiles = (M + kBM - 1) / kBM, kblocks = (K + kBK - 1) / kBK;
+  const int cap = kMaxChainKb * gemm_rotation(c, gemm_n_for(B < 256 ? B : 256));
   double best = 1e30;
-  int best_s = 1;
-  for (int s = 1; s <= c->Smax && s * 4 <= kblocks; ++s) {
+  int best_s = 0;
+  for (int s = 1; s <= c->Smax && (s * 4 <= kblocks || s == 1); ++s) {
+    if ((kblocks + s - 1) / s > cap && s < c->Smax && (s + 1) * 4 <= kblocks) continue;  // chain too long
     const int items = tiles * s;
     const int waves = (items + c->num_sms - 1) / c->num_sms;
     const double eff = (double)items / ((double)waves * c->num_sms);
@@ -384,7 +396,7 @@ int pick_splits(const l2b_ctx* c, int M, int K, int B) {
     const double bytes = (double)M * K * 4 / eff + 2.0 * s * (double)M * B * 4 + waves * 6.0e6;
     if (bytes < best) { best = bytes; best_s = s; }
   }
-  return best_s;
+  return best_s > 0 ? best_s : 1;
 }
 
 int launch_gemm(l2b_ctx* c, int kclass, const float* Wt, int M, int K, const float* Xh, const float* Xl,
