@@ -488,9 +488,18 @@ def main():
         raise SystemExit("bench.py needs a B200: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dist = None
+    host_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # barriers that idle ranks sit in while ONE rank drives all the GPUs must not spin on the
+        # device (an NCCL barrier kernel holds SMs; the persistent-grid kernels need all 148)
+        host_group = dist.new_group(backend="gloo")
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
 
     def barrier():
         torch.cuda.synchronize()
@@ -680,7 +689,7 @@ def main():
             stb["ctx"].close()
         except Exception as e:
             line["batched"] = {"error": str(e)}
-        barrier()
+        host_barrier()
         if rank == 0:
             try:   # the same tensor-parallel group driven by ONE host thread (l2b_create_multi)
                 stg, loopg = run_workload(pkg, args.workload, 0, args.steps, args.warmup, args.seed, B=1,
@@ -689,12 +698,13 @@ def main():
                 msg, _, tokg, _ = loopg(args.steps, pg, tg)
                 line["single_process"] = {"tokens_per_s": args.steps / (msg * 1e-3), "ms_per_step": msg / args.steps,
                                           "same_tokens_as_one_process_per_gpu": bool(np.array_equal(tokg, tok2)),
+                                          "tokens": [int(tokg[0]), int(tok2[0]), int(tg[0]), int(tok[0])],
                                           "call": "l2b_create_multi(hdr, n_gpus=%d, tp_degree=%d, 1, steps): one host "
                                                   "thread, cudaDeviceEnablePeerAccess, no IPC" % (world, world)}
                 stg["ctx"].close()
             except Exception as e:
                 line["single_process"] = {"error": str(e)}
-        barrier()
+        host_barrier()
 
     if rank == 0 and world == 1 and B == 1 and extras:
         others = {}
@@ -777,7 +787,7 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
+        host_barrier()
         dist.destroy_process_group()
     return 0
 

@@ -62,6 +62,14 @@ struct TpParams {
   int wait_idx;                // e_in
   int out_idx;                 // e_out
   int out_off;                 // rank * slice: where this rank's results sit in the gathered vector
+  int skip_wait;               // 1: no griddepcontrol.wait -- every input of this kernel is an LL replica whose
+                               // sequence tags order it behind its producers (local AND remote), so the
+                               // ~4 us between the last CTA of the previous kernel and the release of its
+                               // programmatic dependent leave the critical path.  The step's first kernel
+                               // (token / position / epoch come from the previous step's last kernel) and
+                               // kernels that read plainly stored data keep the wait; a kernel that waits
+                               // triggers its dependents only AFTER the wait, so that "launched" implies
+                               // "the previous step is complete" for every kernel of the step.
   int* ticket;                 // local ticket counter (last CTA publishes)
   int* err;                    // local error word (set on a wait time-out)
   int* peer_flags[kMaxTp];     // &peer.flags[e_out][rank]
@@ -262,7 +270,7 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
   __shared__ int s_bi[WARPS][NB];
   __shared__ int s_is_last;
 
-  griddep_launch_dependents();
+  if (!TP || p.tp.skip_wait) griddep_launch_dependents();
   const bool dbg_on = p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
   long long* dbg_row = dbg_on ? p.dbg + ((size_t)p.dbg_slot * 2 + (blockIdx.x == 0 ? 0 : 1)) * 6 : nullptr;
   if (dbg_on) dbg_row[0] = gtimer_ns();
@@ -310,8 +318,11 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
   if (dbg_on) dbg_row[1] = gtimer_ns();
   if (!TP && p.sync_wait != nullptr) {
     soft_wait(p.sync_wait, p.sync_target);
-  } else {
+  } else if (!TP) {
     griddep_wait();
+  } else if (!p.tp.skip_wait) {
+    griddep_wait();
+    griddep_launch_dependents();
   }
   if (dbg_on) dbg_row[2] = gtimer_ns();
   int tp_seq = 0;

@@ -59,6 +59,7 @@ struct QkvAttnParams {
   const int* tp_epoch;
   int tp_wait_idx, tp_out_idx;
   int xb_off;              // column of head 0 of this rank in the gathered xb
+  int tp_skip_wait;        // see TpParams::skip_wait (layers >= 1: x is an LL replica)
   int* tp_err;
   float* peer_xb[kMaxTp];
 };
@@ -85,7 +86,7 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
   __shared__ float c_max;
   __shared__ double c_sum;
 
-  griddep_launch_dependents();
+  if (!TP || p.tp_skip_wait) griddep_launch_dependents();
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank(), CS = cluster_nctarank();
@@ -133,8 +134,11 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
   // ---- everything below may depend on the previous kernel ----
   if (p.sync_wait != nullptr) {
     soft_wait(p.sync_wait, p.sync_target);
-  } else {
+  } else if (!TP) {
     griddep_wait();
+  } else if (!p.tp_skip_wait) {
+    griddep_wait();
+    griddep_launch_dependents();
   }
   const int pos = ld_act_i32(p.posp);
   const int n_t = pos + 1;

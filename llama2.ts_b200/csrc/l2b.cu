@@ -71,6 +71,8 @@ struct Options {
   int fuse_prefetch = 0; // ... optionally pulling this percentage of wo into L2 while its attention part runs
                          // (measured net-negative: wo 20.0 -> 16.6 us but the fused kernel 46.0 -> 50.6 us)
   int tp_timeout_ms = 20000; // tensor-parallel exchange: bounded spin (see tp_spin_expired)
+  int tp_nowait = 1;         // tensor-parallel kernels whose inputs are all LL replicas skip griddepcontrol.wait
+                             // (TpParams::skip_wait)
   int stream_stages = 0; // mega=2: ring stages per warp (0 = as many as shared memory holds)
   int stream_chunks = 0; // mega=2: attention time chunks per head (0 = SMs / heads, at most 8)
                          // (experiment, opt-in: measured slower than graph+PDL so far)
@@ -163,6 +165,22 @@ struct l2b_ctx {
 };
 
 namespace {
+
+// Every entry point that selects a device restores the caller's current device on return: the
+// host (torch in bench.py, the TS runtime's other native modules) keeps ITS device, also when a
+// context group walked over several.
+struct DevGuard {
+  int prev = -1;
+  DevGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      prev = -1;
+      cudaGetLastError();
+    }
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 int fail(l2b_ctx* c, int code, const char* fmt, ...) {
   char buf[512];
@@ -641,9 +659,11 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
   if (ef < 0) ef = c->weight_bytes > (size_t)100 * 1024 * 1024;
 
   auto flag_on = [&](int g, int e, int src) { return (int*)(c->peer[g] + c->off_flags) + (size_t)e * kMaxTp + src; };
+  const bool nowait = c->opt.tp_nowait != 0 && c->opt.pdl != 0;
   auto fill_tp = [&](TpParams& t, int wait_e, int out_e, size_t out_vec_off, int out_off) {
     memset(&t, 0, sizeof t);
     t.rank = R; t.size = G;
+    t.skip_wait = (nowait && wait_e >= 0) ? 1 : 0;   // layer 0's first kernel (wait_e < 0) reads token/pos/epoch
     t.epoch = c->tp_epoch; t.ticket = c->tp_ticket; t.err = c->tp_err;
     t.ll_in = wait_e >= 0 ? 1 : 0;
     t.wait_idx = wait_e < 0 ? 0 : wait_e;
@@ -721,6 +741,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       f.tp_out_idx = eA;
       f.xb_off = R * Dl;
       f.tp_err = c->tp_err;
+      f.tp_skip_wait = (nowait && l > 0) ? 1 : 0;
       for (int g = 0; g < G; ++g) f.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
       const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
       void* args[] = {&f};
@@ -781,6 +802,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       p.vin = c->xb;
       p.vin_stride = D;
       fill_tp(p.tp, eA, eB, c->off_x, R * Dl);
+      if (l == 0 && fuse) p.tp.skip_wait = 0;   // its old x is the embedding row the fused kernel stored plainly
       int rc = launch_gemv(c, L2B_K_WO, p, 1, st);
       if (rc) return rc;
     }
@@ -1479,6 +1501,7 @@ L2B_API const char* l2b_last_error(const l2b_ctx* ctx) {
 
 static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch, int32_t max_steps,
                          int32_t tp_rank, int32_t tp_size, l2b_ctx** out) {
+  DevGuard dev_guard;
   if (!hdr || !out) return fail(nullptr, L2B_EINVAL, "null hdr/out");
   *out = nullptr;
   const int D = hdr[0], F = hdr[1], L = hdr[2], H = hdr[3];
@@ -1651,6 +1674,7 @@ L2B_API int l2b_create_tp(const int32_t hdr[7], int32_t device, int32_t max_step
 // exchange blocks are mapped into each other with cudaDeviceEnablePeerAccess (no IPC handles).
 L2B_API int l2b_create_multi(const int32_t hdr[7], int32_t n_gpus, int32_t tp_degree, int32_t max_batch,
                              int32_t max_steps, l2b_ctx** out) {
+  DevGuard dev_guard;
   if (!hdr || !out) return fail(nullptr, L2B_EINVAL, "null hdr/out");
   *out = nullptr;
   if (n_gpus < 1 || n_gpus > kMaxTp) return fail(nullptr, L2B_EINVAL, "n_gpus %d outside [1,%d]", n_gpus, kMaxTp);
@@ -1713,6 +1737,7 @@ L2B_API int l2b_create_multi(const int32_t hdr[7], int32_t n_gpus, int32_t tp_de
 }
 
 L2B_API void l2b_destroy(l2b_ctx* c) {
+  DevGuard dev_guard;
   if (!c) return;
   if (!c->kids.empty()) {
     for (l2b_ctx* k : c->kids) {   // nobody may still be spinning on a peer that is being freed
@@ -1812,6 +1837,7 @@ static int placement(l2b_ctx* c, int tensor_id, int layer, Placement* pl) {
 
 L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float* host,
                        uint64_t n_floats) {
+  DevGuard dev_guard;
   if (!c) return L2B_EINVAL;
   if (!host) return fail(c, L2B_EINVAL, "null host pointer");
   if (is_group(c)) {   // replicas keep the whole tensor, tensor-parallel ranks their rows
@@ -1845,6 +1871,7 @@ L2B_API int l2b_upload(l2b_ctx* c, int32_t tensor_id, int32_t layer, const float
 // overlapping the pread of the other, straight into the device layout (w1/w3 interleave,
 // q/k/v stacking).  Shard-aware: a tensor-parallel rank preads only its own rows.
 L2B_API int l2b_load_checkpoint(l2b_ctx* c, const char* path, double* seconds_out) {
+  DevGuard dev_guard;
   if (!c || !path) return L2B_EINVAL;
   if (is_group(c)) {   // every member streams the file (tensor-parallel ranks: only their rows)
     const auto g0 = std::chrono::steady_clock::now();
@@ -1961,6 +1988,7 @@ L2B_API int l2b_weights_ready(const l2b_ctx* c) {
 
 L2B_API int l2b_forward_batch(l2b_ctx* c, int32_t B, const int32_t* tokens, const int32_t* pos,
                               float* logits_out, int32_t* argmax_out) {
+  DevGuard dev_guard;
   int rc = check_ready(c);
   if (rc) return rc;
   if ((rc = check_batch(c, B))) return rc;
@@ -2047,6 +2075,7 @@ static int ensure_prefill(l2b_ctx* c, int cap) {
 
 L2B_API int l2b_prefill(l2b_ctx* c, int32_t seq, int32_t n_tokens, const int32_t* tokens, int32_t pos0,
                         float* logits_out, int32_t* argmax_out) {
+  DevGuard dev_guard;
   int rc = check_ready(c);
   if (rc) return rc;
   if (c->tp_size > 1 || is_tp_group(c))
@@ -2125,6 +2154,7 @@ static int enqueue_sampler(l2b_ctx* c, const float* logits, double temperature, 
 
 L2B_API int l2b_forward_sample(l2b_ctx* c, int32_t token, int32_t pos, double temperature, double topp,
                                float rand01, int32_t* next_out) {
+  DevGuard dev_guard;
   int rc = check_ready(c);
   if (rc) return rc;
   if (!next_out) return fail(c, L2B_EINVAL, "null next_out");
@@ -2153,6 +2183,7 @@ L2B_API int l2b_forward_sample(l2b_ctx* c, int32_t token, int32_t pos, double te
 
 L2B_API int l2b_sample_logits(l2b_ctx* c, const float* logits_host, double temperature, double topp, float rand01,
                               int32_t* next_out) {
+  DevGuard dev_guard;
   if (!c) return L2B_EINVAL;
   if (is_group(c)) return lift(c, c->kids[0], l2b_sample_logits(c->kids[0], logits_host, temperature, topp, rand01, next_out));
   if (!logits_host || !next_out) return fail(c, L2B_EINVAL, "null argument");
@@ -2173,6 +2204,7 @@ L2B_API int l2b_sample_logits(l2b_ctx* c, const float* logits_host, double tempe
 
 L2B_API int l2b_generate_greedy(l2b_ctx* c, int32_t B, const int32_t* tokens, const int32_t* pos,
                                 int32_t n_steps, const int32_t* forced, int32_t* out_tokens) {
+  DevGuard dev_guard;
   int rc = check_ready(c);
   if (rc) return rc;
   if ((rc = check_batch(c, B))) return rc;
@@ -2227,6 +2259,7 @@ L2B_API int64_t l2b_last_launches(const l2b_ctx* c) { return c ? c->last_launche
 
 L2B_API int l2b_profile_batch(l2b_ctx* c, int32_t B, const int32_t* tokens, const int32_t* pos,
                               float* ms_per_class, int32_t* launches_per_class) {
+  DevGuard dev_guard;
   int rc = check_ready(c);
   if (rc) return rc;
   if ((rc = check_batch(c, B))) return rc;
@@ -2284,6 +2317,7 @@ L2B_API int l2b_profile_step(l2b_ctx* c, int32_t token, int32_t pos, float* ms_p
 
 L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer, int32_t pos,
                            float* out, uint64_t n_floats) {
+  DevGuard dev_guard;
   if (!c) return L2B_EINVAL;
   if (!out) return fail(c, L2B_EINVAL, "null out");
   if (seq < 0 || seq >= c->Bmax) return fail(c, L2B_EINVAL, "seq %d", seq);
@@ -2330,6 +2364,7 @@ L2B_API int l2b_read_state(l2b_ctx* c, int32_t which, int32_t seq, int32_t layer
 }
 
 L2B_API int l2b_debug_timeline(l2b_ctx* c, int64_t* out, uint64_t n) {
+  DevGuard dev_guard;
   if (!c || !out) return L2B_EINVAL;
   if (is_group(c)) return lift(c, c->kids[0], l2b_debug_timeline(c->kids[0], out, n));
   CU(c, cudaSetDevice(c->device));
@@ -2345,6 +2380,7 @@ L2B_API int l2b_debug_timeline(l2b_ctx* c, int64_t* out, uint64_t n) {
 }
 
 L2B_API int l2b_reset(l2b_ctx* c) {
+  DevGuard dev_guard;
   if (!c) return L2B_EINVAL;
   if (is_group(c)) {
     for (l2b_ctx* k : c->kids) {
@@ -2364,6 +2400,7 @@ L2B_API int l2b_reset(l2b_ctx* c) {
 }
 
 L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
+  DevGuard dev_guard;
   if (!c || !key) return L2B_EINVAL;
   if (is_group(c)) {
     for (l2b_ctx* k : c->kids) {
@@ -2423,6 +2460,8 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     return write_tp_timeout(c);
+  } else if (k == "tp_nowait") {
+    o.tp_nowait = v != 0;
   } else if (k == "gemv_timeline") {
     if (v && !c->d_dbg2) {
       if (cudaMalloc((void**)&c->d_dbg2, 1024 * 12 * sizeof(long long)) != cudaSuccess) return fail(c, L2B_ENOMEM, "dbg");
@@ -2454,6 +2493,7 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
 }
 
 L2B_API int64_t l2b_tp_export(l2b_ctx* c, void* blob, uint64_t cap) {
+  DevGuard dev_guard;
   if (!c) return L2B_EINVAL;
   if (is_group(c)) return fail(c, L2B_ESTATE, "a single-process group wires its members itself");
   if (c->tp_size <= 1) return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");
@@ -2466,6 +2506,7 @@ L2B_API int64_t l2b_tp_export(l2b_ctx* c, void* blob, uint64_t cap) {
 }
 
 L2B_API int l2b_tp_connect(l2b_ctx* c, const void* blobs, uint64_t blob_bytes, int32_t n_ranks) {
+  DevGuard dev_guard;
   if (!c) return L2B_EINVAL;
   if (is_group(c)) return fail(c, L2B_ESTATE, "a single-process group wires its members itself");
   if (c->tp_size <= 1) return fail(c, L2B_ESTATE, "context was not created with l2b_create_tp");

@@ -105,3 +105,29 @@ def test_single_process_tensor_parallel(pkg, oracle, arch, steps):
         tp.reset()
         assert tp.forward_sample(1, 0, 0.8, 0.9, 0.37) == one.forward_sample(1, 0, 0.8, 0.9, 0.37)
     oracle.set_threads(1)
+
+
+def test_group_upload_from_device_memory_keeps_callers_device(pkg, oracle):
+    """Weights handed over as DEVICE pointers on GPU 0 (l2b_upload copies with cudaMemcpyDefault; the
+    members on other GPUs copy across NVLink), generated tensor by tensor like bench.py does -- and the
+    calling thread's current device is restored by every entry point (a group walks over all GPUs)."""
+    import torch
+    n = 2 if _ngpu() >= 2 else 1
+    hdr, blob = _model(pkg, "wide", 64, 0.04)
+    V, steps = abs(hdr[5]), 8
+    toks = np.concatenate([[1], pkg.synth.teacher_tokens(steps - 1, V, 64)])
+    torch.cuda.set_device(0)
+    with pkg.Context(hdr, n_gpus=n, tp_degree=n, max_batch=1, max_steps=steps) as grp, \
+            pkg.Context(hdr, device=0, max_batch=1, max_steps=steps) as one:
+        for (t, l), a in pkg.synth.slice_blob(hdr, blob).items():
+            ta = torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0") * 1.0   # a kernel produces the tensor
+            torch.cuda.synchronize()                 # synchronises the CURRENT device: must still be 0
+            grp.upload(t, l, ta)
+            assert torch.cuda.current_device() == 0
+            one.upload(t, l, ta)
+            del ta
+        one.set_option("fuse_qkv_attn", 1)
+        for pos in range(steps):
+            a = grp.forward(int(toks[pos]), pos)
+            assert torch.cuda.current_device() == 0
+            assert np.array_equal(a, one.forward(int(toks[pos]), pos)), pos
