@@ -43,6 +43,8 @@ enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
 
 constexpr int kU = 4;          // float4 loads per lane per row per tile
 constexpr int kMaxNB = 8;      // sequences sharing one weight pass
+constexpr int kChunkTiles = 4; // tiles (of 32 lanes x kU float4 = 512 floats) per K-chunk of a row: the unit of the
+                               // canonical summation order and of the intra-CTA split of long rows
 
 // Tensor-parallel exchange (row-sharded projections).  Every rank
 // holds replicas of the gathered vectors (x, xb, hb, logits); a kernel's epilogue stores its
@@ -62,14 +64,6 @@ struct TpParams {
   int wait_idx;                // e_in
   int out_idx;                 // e_out
   int out_off;                 // rank * slice: where this rank's results sit in the gathered vector
-  int skip_wait;               // 1: no griddepcontrol.wait -- every input of this kernel is an LL replica whose
-                               // sequence tags order it behind its producers (local AND remote), so the
-                               // ~4 us between the last CTA of the previous kernel and the release of its
-                               // programmatic dependent leave the critical path.  The step's first kernel
-                               // (token / position / epoch come from the previous step's last kernel) and
-                               // kernels that read plainly stored data keep the wait; a kernel that waits
-                               // triggers its dependents only AFTER the wait, so that "launched" implies
-                               // "the previous step is complete" for every kernel of the step.
   int* ticket;                 // local ticket counter (last CTA publishes)
   int* err;                    // local error word (set on a wait time-out)
   int* peer_flags[kMaxTp];     // &peer.flags[e_out][rank]
@@ -133,6 +127,20 @@ __device__ __forceinline__ float4 ll_load4(const void* base, int j, bool check, 
   return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
 
+// same with the two 16-byte words already requested (several elements' loads in flight at once:
+// the spin of one element must not serialise the L2 round trips of the next ones)
+__device__ __forceinline__ float4 ll_finish4(const void* base, int j, uint4 a, uint4 b, int seq, int* err) {
+  const uint4* b4 = reinterpret_cast<const uint4*>(base) + 2 * (size_t)j;
+  const long long t0 = clock64();
+  int polls = 0;
+  while (!((int)a.y == seq && (int)a.w == seq && (int)b.y == seq && (int)b.w == seq)) {
+    if (tp_spin_expired(t0, err, polls)) break;
+    a = ld_volatile_u4(b4);
+    b = ld_volatile_u4(b4 + 1);
+  }
+  return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
+
 struct GemvParams {
   const float* W;        // [rows][n] row-major, rows even
   int rows;
@@ -170,9 +178,8 @@ struct GemvParams {
   int b0, nact, B;
   int evict_first;
   int l2_prefetch;       // bytes of this CTA's weight range pulled into L2 before griddep_wait()
-  int* work;             // != nullptr: row pairs are handed out dynamically from this counter (zero at
-                         // launch): SMs do not stream at equal rates (GPC sizes differ), a static equal
-                         // split leaves the fast ones idle for ~20 % of the kernel
+  int max_local_pairs;   // upper bound of row pairs per CTA (sizes the chunk-sum scratch in shared memory)
+  int split_k;           // 1: K-chunks of a pair are separate work units (few, long rows per CTA)
   long long* dbg;        // optional per-launch timeline (globaltimer ns): [launch][SM-sampled CTA][6]
   int dbg_slot;
   // software hand-over (common.cuh): wait for `sync_target` arrivals on sync_wait instead of
@@ -264,13 +271,13 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
   typedef XVec<F64> XV;
   typedef typename XV::acc_t acc_t;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];  // [NB] activation vectors
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // [NB] activation vectors | chunk sums | counters
   __shared__ double red_scratch[NB][WARPS];
   __shared__ float s_bv[WARPS][NB];
   __shared__ int s_bi[WARPS][NB];
   __shared__ int s_is_last;
 
-  if (!TP || p.tp.skip_wait) griddep_launch_dependents();
+  griddep_launch_dependents();
   const bool dbg_on = p.dbg != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
   long long* dbg_row = dbg_on ? p.dbg + ((size_t)p.dbg_slot * 2 + (blockIdx.x == 0 ? 0 : 1)) * 6 : nullptr;
   if (dbg_on) dbg_row[0] = gtimer_ns();
@@ -282,34 +289,48 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
   const int pair0 = (int)(((long long)npairs * blockIdx.x) / gridDim.x);
   const int pair1 = (int)(((long long)npairs * (blockIdx.x + 1)) / gridDim.x);
   const int tpp = (n4 + 32 * kU - 1) / (32 * kU);  // tiles per pair
-  const bool dynamic = p.work != nullptr;
-  const int total_warps = (int)gridDim.x * WARPS;
-  // static: this CTA's contiguous range, warps interleaved; dynamic: first pair by global warp id,
-  // every further pair from the shared counter
-  const int my_first = dynamic ? (int)blockIdx.x * WARPS + warp : pair0 + warp;
-  const int limit = dynamic ? npairs : pair1;
+  // Canonical summation order of a row (the same bits whatever grid, thread count, tensor-parallel
+  // degree or work split computes it): lane j of a warp owns the float4 columns j, j+32, ... of the row;
+  // per K-chunk of kChunkTiles tiles it runs two alternating FMA chains and adds their sum to its
+  // running total IN CHUNK ORDER; the row sum is the warp's shuffle tree over the 32 lane totals.
+  // Work unit: a whole row pair -- or, when a CTA owns fewer pairs than it has warps to keep busy
+  // (p.split_k: w2 with its 44 KB rows leaves 2 pairs per CTA on a tensor-parallel rank of 8), one
+  // K-chunk of a pair: the units are dealt to the warps round robin, a chunk's 32 lane sums go to
+  // shared memory, and the warp that completes a pair adds them per lane in chunk order.
+  const int nch = (tpp + kChunkTiles - 1) / kChunkTiles;
+  const bool split = p.split_k != 0 && nch > 1;
+  const int upp = split ? nch : 1;                 // units per pair
+  const int n_units = (pair1 - pair0) * upp;
+  double2* part = reinterpret_cast<double2*>(smem_raw + (size_t)NB * vec_bytes);  // [local pair][chunk][NB][32 lanes]
+  int* done = reinterpret_cast<int*>(part + (size_t)p.max_local_pairs * nch * NB * 32);  // [local pair]
   const float4* W4 = reinterpret_cast<const float4*>(p.W);
   const uint64_t pol = make_l2_policy(p.evict_first != 0);
 
   PairTile cur, nxt;
-  int pair = my_first, jt = 0;
-  if (pair < limit) {
+  int unit = warp;
+  int pair = 0, jt = 0, jend = 0;
+  if (unit < n_units) {
+    const int pl = split ? unit / upp : unit, ch = unit - pl * upp;
+    pair = pair0 + pl;
+    jt = split ? ch * kChunkTiles : 0;
+    jend = split ? (jt + kChunkTiles < tpp ? jt + kChunkTiles : tpp) : tpp;
     const float4* w0 = W4 + (size_t)(2 * pair) * n4;
-    load_pair_tile(cur, w0, w0 + n4, lane, n4, pol);
+    load_pair_tile(cur, w0, w0 + n4, jt * 32 * kU + lane, n4, pol);
   }
+  if (split)
+    for (int i = threadIdx.x; i < pair1 - pair0; i += THREADS) done[i] = 0;
   // The HBM pipe idles between two kernels (tail of the previous one, launch, our prologue).
   // Fill that time: pull the head of this CTA's weight range into L2 now, so that the main
   // loop's next tiles are L2 hits while the stream behind them ramps up.
   if (p.l2_prefetch > 0 && lane == 0) {
     const size_t cta_bytes = (size_t)(pair1 - pair0) * 2 * n * sizeof(float);
-    const int pf_pair0 = dynamic ? (int)blockIdx.x * WARPS : pair0;
     size_t want = (size_t)p.l2_prefetch < cta_bytes ? (size_t)p.l2_prefetch : cta_bytes;
     const size_t per = ((want / WARPS) + 15) & ~(size_t)15;
     const size_t off = (size_t)warp * per;
     if (per > 0 && off < want) {
       const size_t len = (off + per <= want) ? per : ((want - off) & ~(size_t)15);
       if (len > 0)
-        prefetch_l2_bulk(reinterpret_cast<const unsigned char*>(p.W) + (size_t)pf_pair0 * 2 * n * sizeof(float) + off,
+        prefetch_l2_bulk(reinterpret_cast<const unsigned char*>(p.W) + (size_t)pair0 * 2 * n * sizeof(float) + off,
                          (uint32_t)len);
     }
   }
@@ -318,11 +339,8 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
   if (dbg_on) dbg_row[1] = gtimer_ns();
   if (!TP && p.sync_wait != nullptr) {
     soft_wait(p.sync_wait, p.sync_target);
-  } else if (!TP) {
+  } else {
     griddep_wait();
-  } else if (!p.tp.skip_wait) {
-    griddep_wait();
-    griddep_launch_dependents();
   }
   if (dbg_on) dbg_row[2] = gtimer_ns();
   int tp_seq = 0;
@@ -343,8 +361,7 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
         if (p.tok_emb != nullptr) src = p.tok_emb + (size_t)ld_act_i32(p.tokp + b) * n;
         const float4* src4 = reinterpret_cast<const float4*>(src);
         const bool write_x = (p.tok_emb != nullptr) && blockIdx.x == 0;
-        for (int j = threadIdx.x; j < n4; j += THREADS) {
-          const float4 v = ll_in ? ll_load4(p.vin, j, true, seq_in, p.tp.err) : ld_act4(src4 + j);
+        auto consume = [&](int j, float4 v) {
           if (PRO == PRO_COPY) {
             XV::store(xs, n4, j, v);
           } else {
@@ -361,6 +378,28 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
               reinterpret_cast<float4*>(p.x + (size_t)b * p.xdim)[j] = v;
             }
           }
+        };
+        if (ll_in) {   // tagged replica: four elements' words in flight per thread before the first spin
+          constexpr int BL = 4;
+          for (int j0 = threadIdx.x; j0 < n4; j0 += BL * THREADS) {
+            uint4 wa[BL], wb[BL];
+#pragma unroll
+            for (int k = 0; k < BL; ++k) {
+              const int j = j0 + k * THREADS;
+              if (j < n4) {
+                const uint4* b4 = reinterpret_cast<const uint4*>(p.vin) + 2 * (size_t)j;
+                wa[k] = ld_volatile_u4(b4);
+                wb[k] = ld_volatile_u4(b4 + 1);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < BL; ++k) {
+              const int j = j0 + k * THREADS;
+              if (j < n4) consume(j, ll_finish4(p.vin, j, wa[k], wb[k], seq_in, p.tp.err));
+            }
+          }
+        } else {
+          for (int j = threadIdx.x; j < n4; j += THREADS) consume(j, ld_act4(src4 + j));
         }
       } else {
         for (int j = threadIdx.x; j < n4; j += THREADS) XV::store(xs, n4, j, f4_zero());
@@ -412,30 +451,96 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
   float bv = -INFINITY;
   int bi = 0x7fffffff;
 
-  acc_t acc[2][NB][KACC];
-#pragma unroll
-  for (int s = 0; s < NB; ++s)
-#pragma unroll
-    for (int k = 0; k < KACC; ++k) acc[0][s][k] = acc[1][s][k] = (acc_t)0;
-
-  bool have = pair < limit;
-  int next_pair = 0;
-  while (have) {
-    if (jt == 0) {  // the pair after this one: the atomic is issued now, its result is only
-                    // consumed when the last tile of the current pair is reached (latency hidden)
-      if (dynamic) {
-        if (lane == 0) next_pair = atomicAdd(p.work, 1) + total_warps;
+  // pair epilogue, run by the lanes s < nact of ONE warp with the finished sums of "their" sequence
+  auto pair_epilogue = [&](int pair, double m0, double m1) {
+    const float s0 = (float)m0, s1 = (float)m1;  // xout[i] = sum, llama2.ts:201
+    const int r = 2 * pair;
+    if (EPI == EPI_QKV) {
+      const int seg = r / p.Dq, i = r - seg * p.Dq;
+      const int h = i / p.hs, c = i - h * p.hs;
+      const size_t row = (size_t)eb * p.kv_seq_stride + ((size_t)h * p.steps + pos) * p.hs + c;
+      if (seg == 2) {  // value row pair, llama2.ts:240
+        p.vc[row] = s0;
+        p.vc[row + 1] = s1;
+      } else {  // RoPE, llama2.ts:224-235 (table row from the checkpoint)
+        const double fr = (double)__ldg(p.fcr + (size_t)pos * (p.hs / 2) + c / 2);
+        const double fi = (double)__ldg(p.fci + (size_t)pos * (p.hs / 2) + c / 2);
+        const float o0 = (float)((double)s0 * fr - (double)s1 * fi);
+        const float o1 = (float)((double)s0 * fi + (double)s1 * fr);
+        float* dst = seg == 0 ? p.q + (size_t)eb * p.Dq + i : p.kc + row;
+        dst[0] = o0;
+        dst[1] = o1;
+      }
+    } else if (EPI == EPI_RESID) {
+      // accum(x, xb2), llama2.ts:168-170,273,295
+      if (TP) {
+        const int gi = p.tp.out_off + r;  // index in the replicated residual stream (LL words)
+        const uint4 old = ld_volatile_u4(reinterpret_cast<const uint4*>(p.x) + (gi >> 1));
+        const float n0 = (float)((double)__uint_as_float(old.x) + (double)s0);
+        const float n1 = (float)((double)__uint_as_float(old.z) + (double)s1);
+        const uint32_t sq = (uint32_t)(tp_seq + p.tp.out_idx);
+        for (int g = 0; g < p.tp.size; ++g)
+          st_sys_u4(reinterpret_cast<uint4*>(p.tp.peer_out[g]) + (gi >> 1), __float_as_uint(n0), sq,
+                    __float_as_uint(n1), sq);
       } else {
-        next_pair = pair + WARPS;
+        float* xr = p.x + (size_t)eb * p.xdim + r;
+        xr[0] = (float)((double)xr[0] + (double)s0);
+        xr[1] = (float)((double)xr[1] + (double)s1);
+      }
+    } else if (EPI == EPI_SWIGLU) {
+      // rows interleaved on upload: 2i = w1 row i, 2i+1 = w3 row i.  llama2.ts:284-289
+      const double hv = (double)s0;
+      const float silu = (float)(hv * (1.0 / (1.0 + exp(-hv))));
+      const float hv2 = (float)((double)silu * (double)s1);
+      if (TP) {
+        const uint32_t sq = (uint32_t)(tp_seq + p.tp.out_idx);
+        for (int g = 0; g < p.tp.size; ++g)
+          st_sys_u2(reinterpret_cast<uint2*>(p.tp.peer_out[g]) + p.tp.out_off + pair, __float_as_uint(hv2), sq);
+      } else {
+        p.hb[(size_t)eb * p.hb_stride + pair] = hv2;
+      }
+    } else {
+      if (TP) {
+        for (int g = 0; g < p.tp.size; ++g) {
+          st_relaxed_sys_f32(p.tp.peer_out[g] + p.tp.out_off + r, s0);
+          st_relaxed_sys_f32(p.tp.peer_out[g] + p.tp.out_off + r + 1, s1);
+        }
+        argmax_consider(s0, p.tp.out_off + r, bv, bi);      // global vocabulary index
+        argmax_consider(s1, p.tp.out_off + r + 1, bv, bi);
+      } else {
+        float* lg = p.logits + (size_t)eb * p.V + r;
+        lg[0] = s0;
+        lg[1] = s1;
+        argmax_consider(s0, r, bv, bi);
+        argmax_consider(s1, r + 1, bv, bi);
       }
     }
-    // request the next tile before touching the current one
-    int npair = pair, njt = jt + 1;
-    if (njt == tpp) {
-      njt = 0;
-      npair = dynamic ? __shfl_sync(0xffffffffu, next_pair, 0) : next_pair;
+  };
+
+  acc_t acc[2][NB][KACC];
+  double lt[2][NB];   // this lane's running totals (chunk order)
+#pragma unroll
+  for (int s = 0; s < NB; ++s) {
+    lt[0][s] = lt[1][s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < KACC; ++k) acc[0][s][k] = acc[1][s][k] = (acc_t)0;
+  }
+
+  bool have = unit < n_units;
+  while (have) {
+    // request the next tile (same unit, or the first tile of this warp's next unit) before touching
+    // the current one
+    int nunit = unit, npair = pair, njt = jt + 1, njend = jend;
+    if (njt == jend) {
+      nunit = unit + WARPS;
+      if (nunit < n_units) {
+        const int pl = split ? nunit / upp : nunit, ch = nunit - pl * upp;
+        npair = pair0 + pl;
+        njt = split ? ch * kChunkTiles : 0;
+        njend = split ? (njt + kChunkTiles < tpp ? njt + kChunkTiles : tpp) : tpp;
+      }
     }
-    const bool more = npair < limit;
+    const bool more = nunit < n_units;
     if (more) {
       const float4* w0 = W4 + (size_t)(2 * npair) * n4;
       load_pair_tile(nxt, w0, w0 + n4, njt * 32 * kU + lane, n4, pol);
@@ -469,92 +574,69 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
         }
       }
     }
-
-    if (jt == tpp - 1) {
-      double m0 = 0.0, m1 = 0.0;  // the sums of "my" sequence (lane s <-> sequence s)
+    if ((jt + 1) % kChunkTiles == 0 || jt == tpp - 1) {  // K-chunk complete: chains -> lane totals
 #pragma unroll
       for (int s = 0; s < NB; ++s) {
-        double d0 = 0.0, d1 = 0.0;
+        double c0 = 0.0, c1 = 0.0;
 #pragma unroll
         for (int k = 0; k < KACC; ++k) {
-          d0 += (double)acc[0][s][k];
-          d1 += (double)acc[1][s][k];
+          c0 += (double)acc[0][s][k];
+          c1 += (double)acc[1][s][k];
           acc[0][s][k] = acc[1][s][k] = (acc_t)0;
         }
-        d0 = warp_sum_f64(d0);
-        d1 = warp_sum_f64(d1);
-        if (lane == s) {
-          m0 = d0;
-          m1 = d1;
-        }
-      }
-      if (epi_lane) {
-        const float s0 = (float)m0, s1 = (float)m1;  // xout[i] = sum, llama2.ts:201
-        const int r = 2 * pair;
-        if (EPI == EPI_QKV) {
-          const int seg = r / p.Dq, i = r - seg * p.Dq;
-          const int h = i / p.hs, c = i - h * p.hs;
-          const size_t row = (size_t)eb * p.kv_seq_stride + ((size_t)h * p.steps + pos) * p.hs + c;
-          if (seg == 2) {  // value row pair, llama2.ts:240
-            p.vc[row] = s0;
-            p.vc[row + 1] = s1;
-          } else {  // RoPE, llama2.ts:224-235 (table row from the checkpoint)
-            const double fr = (double)__ldg(p.fcr + (size_t)pos * (p.hs / 2) + c / 2);
-            const double fi = (double)__ldg(p.fci + (size_t)pos * (p.hs / 2) + c / 2);
-            const float o0 = (float)((double)s0 * fr - (double)s1 * fi);
-            const float o1 = (float)((double)s0 * fi + (double)s1 * fr);
-            float* dst = seg == 0 ? p.q + (size_t)eb * p.Dq + i : p.kc + row;
-            dst[0] = o0;
-            dst[1] = o1;
-          }
-        } else if (EPI == EPI_RESID) {
-          // accum(x, xb2), llama2.ts:168-170,273,295
-          if (TP) {
-            const int gi = p.tp.out_off + r;  // index in the replicated residual stream (LL words)
-            const uint4 old = ld_volatile_u4(reinterpret_cast<const uint4*>(p.x) + (gi >> 1));
-            const float n0 = (float)((double)__uint_as_float(old.x) + (double)s0);
-            const float n1 = (float)((double)__uint_as_float(old.z) + (double)s1);
-            const uint32_t sq = (uint32_t)(tp_seq + p.tp.out_idx);
-            for (int g = 0; g < p.tp.size; ++g)
-              st_sys_u4(reinterpret_cast<uint4*>(p.tp.peer_out[g]) + (gi >> 1), __float_as_uint(n0), sq,
-                        __float_as_uint(n1), sq);
-          } else {
-            float* xr = p.x + (size_t)eb * p.xdim + r;
-            xr[0] = (float)((double)xr[0] + (double)s0);
-            xr[1] = (float)((double)xr[1] + (double)s1);
-          }
-        } else if (EPI == EPI_SWIGLU) {
-          // rows interleaved on upload: 2i = w1 row i, 2i+1 = w3 row i.  llama2.ts:284-289
-          const double hv = (double)s0;
-          const float silu = (float)(hv * (1.0 / (1.0 + exp(-hv))));
-          const float hv2 = (float)((double)silu * (double)s1);
-          if (TP) {
-            const uint32_t sq = (uint32_t)(tp_seq + p.tp.out_idx);
-            for (int g = 0; g < p.tp.size; ++g)
-              st_sys_u2(reinterpret_cast<uint2*>(p.tp.peer_out[g]) + p.tp.out_off + pair, __float_as_uint(hv2), sq);
-          } else {
-            p.hb[(size_t)eb * p.hb_stride + pair] = hv2;
-          }
-        } else {
-          if (TP) {
-            for (int g = 0; g < p.tp.size; ++g) {
-              st_relaxed_sys_f32(p.tp.peer_out[g] + p.tp.out_off + r, s0);
-              st_relaxed_sys_f32(p.tp.peer_out[g] + p.tp.out_off + r + 1, s1);
-            }
-            argmax_consider(s0, p.tp.out_off + r, bv, bi);      // global vocabulary index
-            argmax_consider(s1, p.tp.out_off + r + 1, bv, bi);
-          } else {
-            float* lg = p.logits + (size_t)eb * p.V + r;
-            lg[0] = s0;
-            lg[1] = s1;
-            argmax_consider(s0, r, bv, bi);
-            argmax_consider(s1, r + 1, bv, bi);
-          }
-        }
+        lt[0][s] += c0;
+        lt[1][s] += c1;
       }
     }
+
+    if (jt == jend - 1) {  // unit complete
+      const int pl = pair - pair0;
+      bool run_epi = !split;
+      if (split) {
+        // publish this chunk's lane sums; the warp that completes the pair adds the chunks per lane in
+        // chunk order (below) while the other warps keep streaming
+        const int ch = unit - pl * upp;
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+          part[(((size_t)pl * nch + ch) * NB + s) * 32 + lane] = make_double2(lt[0][s], lt[1][s]);
+          lt[0][s] = lt[1][s] = 0.0;
+        }
+        __threadfence_block();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) old = atomicAdd(done + pl, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == nch - 1) {
+          __threadfence_block();
+          run_epi = true;
+#pragma unroll
+          for (int s = 0; s < NB; ++s)
+            for (int c2 = 0; c2 < nch; ++c2) {
+              const double2 v = part[(((size_t)pl * nch + c2) * NB + s) * 32 + lane];
+              lt[0][s] += v.x;
+              lt[1][s] += v.y;
+            }
+        }
+      }
+      if (run_epi) {
+        double m0 = 0.0, m1 = 0.0;  // the sums of "my" sequence (lane s <-> sequence s)
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+          const double d0 = warp_sum_f64(lt[0][s]);
+          const double d1 = warp_sum_f64(lt[1][s]);
+          lt[0][s] = lt[1][s] = 0.0;
+          if (lane == s) {
+            m0 = d0;
+            m1 = d1;
+          }
+        }
+        if (epi_lane) pair_epilogue(pair, m0, m1);
+      }
+    }
+    unit = nunit;
     pair = npair;
     jt = njt;
+    jend = njend;
     cur = nxt;
     have = more;
   }

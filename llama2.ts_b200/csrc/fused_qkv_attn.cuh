@@ -59,7 +59,6 @@ struct QkvAttnParams {
   const int* tp_epoch;
   int tp_wait_idx, tp_out_idx;
   int xb_off;              // column of head 0 of this rank in the gathered xb
-  int tp_skip_wait;        // see TpParams::skip_wait (layers >= 1: x is an LL replica)
   int* tp_err;
   float* peer_xb[kMaxTp];
 };
@@ -86,7 +85,7 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
   __shared__ float c_max;
   __shared__ double c_sum;
 
-  if (!TP || p.tp_skip_wait) griddep_launch_dependents();
+  griddep_launch_dependents();
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank(), CS = cluster_nctarank();
@@ -134,11 +133,8 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
   // ---- everything below may depend on the previous kernel ----
   if (p.sync_wait != nullptr) {
     soft_wait(p.sync_wait, p.sync_target);
-  } else if (!TP) {
+  } else {
     griddep_wait();
-  } else if (!p.tp_skip_wait) {
-    griddep_wait();
-    griddep_launch_dependents();
   }
   const int pos = ld_act_i32(p.posp);
   const int n_t = pos + 1;
@@ -219,6 +215,7 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
 
   {
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    double tot0 = 0.0, tot1 = 0.0;
     int jt = 0;
     bool have = pi < pi1;
     while (have) {
@@ -254,10 +251,14 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
           }
         }
       }
-      if (jt == tpp - 1) {
-        const double d0 = warp_sum_f64(acc[0][0] + acc[0][1]);
-        const double d1 = warp_sum_f64(acc[1][0] + acc[1][1]);
+      if ((jt + 1) % kChunkTiles == 0 || jt == tpp - 1) {   // a K-chunk is complete: the canonical summation
+        tot0 += acc[0][0] + acc[0][1];                      // order of l2b_rowpair_matvec_kernel (lane totals in
+        tot1 += acc[1][0] + acc[1][1];                      // chunk order, then one shuffle tree): same bits
         acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.0;
+      }
+      if (jt == tpp - 1) {
+        const double d0 = warp_sum_f64(tot0), d1 = warp_sum_f64(tot1);
+        tot0 = tot1 = 0.0;
         if (lane == 0) {
           const float s0 = (float)d0, s1 = (float)d1;
           const int seg = pi / half, c = 2 * (pi - seg * half);

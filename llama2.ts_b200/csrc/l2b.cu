@@ -55,9 +55,6 @@ struct Options {
   int attn_warp = 2048;  // batched path: one-warp-per-(sequence, head) attention kernel when there are at
                          // least this many (sequence, head) pairs (0 = never); below, the cluster kernel
   int tc_tmem_a = 1;     // N <= 128: weight operand in tensor memory (l2b_tc3x_tmemA_matmul_kernel)
-  int dyn_sched = 0;         // batch-1 GEMV kernels hand out row pairs dynamically (see GemvParams::work);
-                             // measured: CTAs finish together, but 193 vs 199 tok/s -- under PDL the next
-                             // kernel's prefetch already fills the SMs that finish early
   int l2_prefetch = 262144;  // bytes per CTA prefetched into L2 before griddep_wait (0 = off)
   int attn_prefetch = 0;     // attention kernel prefetches the wo weights into L2 (measured net-negative: it
                              // delays the K/V copies in the same queue; kept as an option)
@@ -71,8 +68,6 @@ struct Options {
   int fuse_prefetch = 0; // ... optionally pulling this percentage of wo into L2 while its attention part runs
                          // (measured net-negative: wo 20.0 -> 16.6 us but the fused kernel 46.0 -> 50.6 us)
   int tp_timeout_ms = 20000; // tensor-parallel exchange: bounded spin (see tp_spin_expired)
-  int tp_nowait = 1;         // tensor-parallel kernels whose inputs are all LL replicas skip griddepcontrol.wait
-                             // (TpParams::skip_wait)
   int stream_stages = 0; // mega=2: ring stages per warp (0 = as many as shared memory holds)
   int stream_chunks = 0; // mega=2: attention time chunks per head (0 = SMs / heads, at most 8)
                          // (experiment, opt-in: measured slower than graph+PDL so far)
@@ -109,11 +104,9 @@ struct l2b_ctx {
   float* blk_val = nullptr;
   int* blk_idx = nullptr;
   int *d_forced = nullptr, *d_out = nullptr;
-  int* d_work = nullptr;      // dynamic-schedule counters, one per GEMV launch of a step
   int* d_sync = nullptr;      // software hand-over counters, one per kernel of a batch-1 step
   int sync_idx = -1, sync_prev_grid = 0; // chain state while a batch-1 step is being enqueued (-1: off)
-  int work_idx = 0, work_cap = 0;
-  bool work_armed = false;    // counters were zeroed for the launches being enqueued right now
+  int work_cap = 0;           // entries of d_sync
   unsigned* d_bar = nullptr;  // grid barrier words of the persistent kernel
   uint2* d_ll = nullptr;      // streaming kernel: LL exchange words {value, sequence}; last word: error flag
   size_t ll_words = 0;
@@ -330,12 +323,31 @@ int pick_nb(const l2b_ctx* c, int B, int n) {
   return nb;
 }
 
+// K-chunks of a row pair become separate work units when a CTA owns too few pairs to keep its warps
+// streaming (GemvParams::split_k); their lane sums travel through shared memory behind the activation
+// vectors: [local pair][chunk][nb][32 lanes] double2 + per-pair counters.  Returns the scratch bytes.
+size_t gemv_scratch_bytes(GemvParams& p, int grid, int nb, int threads, size_t vec_bytes) {
+  const int n4 = p.n / 4, tpp = (n4 + 32 * kU - 1) / (32 * kU), nch = (tpp + kChunkTiles - 1) / kChunkTiles;
+  const int warps = threads / 32;
+  p.max_local_pairs = (p.rows / 2 + grid - 1) / grid + 1;
+  p.split_k = 0;
+  // whole pairs as long as at least half the warps get one (measured on one GPU, 7B: wo/w2 with 13.8
+  // pairs per 16-warp CTA are faster unsplit, 36.4 vs 38.2 us for w2)
+  if (nch <= 1 || p.rows / 2 >= (long long)grid * warps / 2) return 0;
+  const size_t bytes = (size_t)p.max_local_pairs * nch * nb * 32 * sizeof(double2) +
+                       (((size_t)p.max_local_pairs * sizeof(int)) + 15) / 16 * 16;
+  if (vec_bytes + bytes > 200 * 1024) return 0;
+  p.split_k = 1;
+  return bytes;
+}
+
 int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
   if (c->tp_size > 1) {
     gemv_fn fn = pick_kernel_tp(kclass);
-    p.B = 1; p.b0 = 0; p.nact = 1; p.work = nullptr; p.dbg = nullptr;
+    p.B = 1; p.b0 = 0; p.nact = 1; p.dbg = nullptr;
+    const size_t smem = (size_t)p.n * 8 + gemv_scratch_bytes(p, c->num_sms, 1, 512, (size_t)p.n * 8);
     void* args[] = {&p};
-    return launch(c, kclass, (const void*)fn, dim3(c->num_sms), dim3(512), (size_t)p.n * 8, 1, args, st);
+    return launch(c, kclass, (const void*)fn, dim3(c->num_sms), dim3(512), smem, 1, args, st);
   }
   p.dbg = nullptr;
   if (c->gemv_dbg_arm && c->d_dbg2 && c->gemv_dbg_slot < 1024) {
@@ -364,13 +376,12 @@ int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
     c->sync_idx++;
     c->sync_prev_grid = grid;
   }
-  p.work = nullptr;
-  if (c->work_armed && nb == 1 && B == 1 && c->work_idx < c->work_cap) p.work = c->d_work + c->work_idx++;
+  const size_t smem = nb * per + gemv_scratch_bytes(p, grid, nb, threads, nb * per);
   for (int b0 = 0; b0 < B; b0 += nb) {
     p.b0 = b0;
     p.nact = (B - b0) < nb ? (B - b0) : nb;
     void* args[] = {&p};
-    int rc = launch(c, kclass, (const void*)fn, dim3(grid), dim3(threads), nb * per, 1, args, st);
+    int rc = launch(c, kclass, (const void*)fn, dim3(grid), dim3(threads), smem, 1, args, st);
     if (rc) return rc;
   }
   return 0;
@@ -659,11 +670,9 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
   if (ef < 0) ef = c->weight_bytes > (size_t)100 * 1024 * 1024;
 
   auto flag_on = [&](int g, int e, int src) { return (int*)(c->peer[g] + c->off_flags) + (size_t)e * kMaxTp + src; };
-  const bool nowait = c->opt.tp_nowait != 0 && c->opt.pdl != 0;
   auto fill_tp = [&](TpParams& t, int wait_e, int out_e, size_t out_vec_off, int out_off) {
     memset(&t, 0, sizeof t);
     t.rank = R; t.size = G;
-    t.skip_wait = (nowait && wait_e >= 0) ? 1 : 0;   // layer 0's first kernel (wait_e < 0) reads token/pos/epoch
     t.epoch = c->tp_epoch; t.ticket = c->tp_ticket; t.err = c->tp_err;
     t.ll_in = wait_e >= 0 ? 1 : 0;
     t.wait_idx = wait_e < 0 ? 0 : wait_e;
@@ -741,7 +750,6 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       f.tp_out_idx = eA;
       f.xb_off = R * Dl;
       f.tp_err = c->tp_err;
-      f.tp_skip_wait = (nowait && l > 0) ? 1 : 0;
       for (int g = 0; g < G; ++g) f.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
       const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
       void* args[] = {&f};
@@ -802,7 +810,6 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       p.vin = c->xb;
       p.vin_stride = D;
       fill_tp(p.tp, eA, eB, c->off_x, R * Dl);
-      if (l == 0 && fuse) p.tp.skip_wait = 0;   // its old x is the embedding row the fused kernel stored plainly
       int rc = launch_gemv(c, L2B_K_WO, p, 1, st);
       if (rc) return rc;
     }
@@ -904,13 +911,6 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   base.blk_idx = c->blk_idx;
   base.evict_first = ef;
   base.l2_prefetch = ef ? c->opt.l2_prefetch : 0;  // L2-resident models need no prefetch
-
-  c->work_idx = 0;
-  c->work_armed = false;
-  if (c->opt.dyn_sched && B == 1) {
-    CU(c, cudaMemsetAsync(c->d_work, 0, sizeof(int) * (size_t)c->work_cap, st));
-    c->work_armed = true;
-  }
 
   const int cs = auto_cluster(c, B);
   // fused q/k/v + attention: one cluster per head
@@ -1057,7 +1057,6 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
     p.logits = c->logits;
     p.V = c->V;
     int rc = launch_gemv(c, L2B_K_CLS, p, B, st);
-    c->work_armed = false;
     c->sync_idx = -1;
     if (rc) return rc;
   }
@@ -1625,7 +1624,6 @@ static int create_common(const int32_t hdr[7], int32_t device, int32_t max_batch
   }
   TRY(dev_alloc(c, &c->d_bar, 4, true));
   c->work_cap = 4 * L + 8;
-  TRY(dev_alloc(c, &c->d_work, (size_t)c->work_cap, true));
   TRY(dev_alloc(c, &c->d_sync, (size_t)c->work_cap, true));
   TRY(dev_alloc(c, &c->samp_f, 4 * sV, true));
   TRY(dev_alloc(c, &c->samp_i, 2 * sV, true));
@@ -1768,7 +1766,7 @@ L2B_API void l2b_destroy(l2b_ctx* c) {
                  c->pf_x, c->pf_xb, c->pf_q, c->Wt};
   for (float* p : fl)
     if (p) cudaFree(p);
-  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->d_work, c->d_sync, c->samp_i, (int*)c->samp_f,
+  int* il[] = {c->d_ctl, c->d_dev, c->blk_idx, c->d_forced, c->d_out, (int*)c->d_bar, c->d_sync, c->samp_i, (int*)c->samp_f,
                (int*)c->d_ll, (int*)c->d_dbg, (int*)c->d_dbg2};
   for (int* p : il)
     if (p) cudaFree(p);
@@ -2429,8 +2427,6 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     o.evict_first = v < 0 ? -1 : (v != 0);
   } else if (k == "tc_min_batch") {
     o.tc_min_batch = v < 0 ? 0 : v;
-  } else if (k == "dyn_sched") {
-    o.dyn_sched = v != 0;
   } else if (k == "l2_prefetch") {
     o.l2_prefetch = v < 0 ? 0 : v;
   } else if (k == "attn_prefetch") {
@@ -2460,8 +2456,6 @@ L2B_API int l2b_set_option(l2b_ctx* c, const char* key, int64_t value) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     return write_tp_timeout(c);
-  } else if (k == "tp_nowait") {
-    o.tp_nowait = v != 0;
   } else if (k == "gemv_timeline") {
     if (v && !c->d_dbg2) {
       if (cudaMalloc((void**)&c->d_dbg2, 1024 * 12 * sizeof(long long)) != cudaSuccess) return fail(c, L2B_ENOMEM, "dbg");

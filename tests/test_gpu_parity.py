@@ -211,7 +211,7 @@ def test_variants_agree(pkg, oracle):
     base = run()
     for opts in ({"graph": 0}, {"pdl": 0}, {"graph": 0, "pdl": 0}, {"threads": 256},
                  {"threads": 256, "ctas_per_sm": 2}, {"attn_cluster": 1}, {"attn_cluster": 2},
-                 {"evict_first": 1}, {"dyn_sched": 1}, {"l2_prefetch": 0}, {"soft_sync": 1},
+                 {"evict_first": 1}, {"l2_prefetch": 0}, {"soft_sync": 1},
                  {"soft_sync": 1, "graph": 0}, {"fuse_prefetch": 100}):
         for k, v in opts.items():
             ctx.set_option(k, v)
@@ -222,7 +222,7 @@ def test_variants_agree(pkg, oracle):
             assert all(np.array_equal(a, b) for a, b in zip(got, base)), opts
         for k in opts:
             ctx.set_option(k, {"graph": 1, "pdl": 1, "threads": 512, "ctas_per_sm": 1,
-                               "attn_cluster": 0, "evict_first": -1, "dyn_sched": 0, "l2_prefetch": 262144,
+                               "attn_cluster": 0, "evict_first": -1, "l2_prefetch": 262144,
                                "soft_sync": 0, "fuse_prefetch": 0}[k])
     # separate q/k/v and attention kernels (the default fuses them per head in one cluster kernel):
     # same GEMV arithmetic, attention sums in a different order -> tolerance; pos 0 is exact

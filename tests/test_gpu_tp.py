@@ -68,13 +68,6 @@ for fuse in (0, 1):                      # the stand-alone kernels on both sides
     a2 = ctx.generate_greedy([1], [0], steps, forced)[:, 0]
     b2 = single.generate_greedy([1], [0], steps, forced)[:, 0]
     assert np.array_equal(a2, b2) and np.array_equal(a2, a), (rank, fuse, a2, b2)
-ctx.reset()
-ctx.set_option("tp_nowait", 0)           # every kernel behind griddepcontrol.wait: same bits
-a3 = ctx.generate_greedy([1], [0], steps, forced)[:, 0]
-assert np.array_equal(a3, a), (rank, "tp_nowait=0", a3, a)
-ctx.set_option("tp_nowait", 1)
-ctx.reset()
-ctx.generate_greedy([1], [0], steps, forced)
 ms_tp, ms_one = ctx.last_device_ms() / steps, single.last_device_ms() / steps
 dist.barrier()
 print("rank %%d ok: max|dlogit| %%.3g, bit-identical to 1 GPU, %%.3f ms/step (1 GPU %%.3f)" %% (rank, worst, ms_tp, ms_one))

@@ -16,11 +16,14 @@ case "$what" in
           python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
             bench.py --gpus $n "$@" > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
           tail -c 6000 gpurun_out/bench_n$n.json; tail -20 gpurun_out/bench_n$n.err ;;
-  launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches.csv \
-            python bench.py --no-others --no-cpu-baseline "$@" > gpurun_out/ncu_launches.log 2>&1; tail -3 gpurun_out/ncu_launches.log ;;
-  ncu)    k=$1; shift
-          ncu --set full --clock-control none --import-source on -k "regex:$k" -c 6 -o gpurun_out/prof -f \
-            python bench.py --no-others --no-cpu-baseline "$@" > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
+  launches) # the first ~1000 launches are torch's weight generation + the warm-up steps
+          ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1000 -c 400 --csv \
+            --log-file gpurun_out/launches.csv python bench.py --steps 4 --warmup 3 --no-others --no-cpu-baseline "$@" \
+            > gpurun_out/ncu_launches.log 2>&1; tail -3 gpurun_out/ncu_launches.log ;;
+  ncu)    k=$1; shift   # e.g. "rowpair_matvec|qkv_attn": skips the first two steps of matching kernels
+          ncu --set full --clock-control none --import-source on -k "regex:$k" --launch-skip 260 -c 10 -o gpurun_out/prof -f \
+            python bench.py --steps 4 --warmup 3 --no-others --no-cpu-baseline "$@" > gpurun_out/ncu_full.log 2>&1
+          tail -3 gpurun_out/ncu_full.log ;;
   sanitizer) tool=$1; shift
           timeout 900 compute-sanitizer --tool $tool --error-exitcode 0 python "$@" > gpurun_out/sanitizer_$tool.log 2>&1
           tail -15 gpurun_out/sanitizer_$tool.log ;;
