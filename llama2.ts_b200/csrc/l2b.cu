@@ -331,9 +331,13 @@ size_t gemv_scratch_bytes(GemvParams& p, int grid, int nb, int threads, size_t v
   const int warps = threads / 32;
   p.max_local_pairs = (p.rows / 2 + grid - 1) / grid + 1;
   p.split_k = 0;
-  // whole pairs as long as at least half the warps get one (measured on one GPU, 7B: wo/w2 with 13.8
-  // pairs per 16-warp CTA are faster unsplit, 36.4 vs 38.2 us for w2)
-  if (nch <= 1 || p.rows / 2 >= (long long)grid * warps / 2) return 0;
+  if (nch <= 1) return 0;
+  // critical path of a CTA in tile times: whole pairs vs K-chunks as units; split only for a clear win
+  // (measured on one GPU, 7B: w2 with 13.8 pairs per 16-warp CTA is faster unsplit, 36.4 vs 38.2 us)
+  const int lp = (p.rows / 2 + grid - 1) / grid;
+  const int whole = ((lp + warps - 1) / warps) * tpp;
+  const int chunks = ((lp * nch + warps - 1) / warps) * kChunkTiles;
+  if (chunks * 10 > whole * 8) return 0;
   const size_t bytes = (size_t)p.max_local_pairs * nch * nb * 32 * sizeof(double2) +
                        (((size_t)p.max_local_pairs * sizeof(int)) + 15) / 16 * 16;
   if (vec_bytes + bytes > 200 * 1024) return 0;
@@ -345,6 +349,10 @@ int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
   if (c->tp_size > 1) {
     gemv_fn fn = pick_kernel_tp(kclass);
     p.B = 1; p.b0 = 0; p.nact = 1; p.dbg = nullptr;
+    if (c->gemv_dbg_arm && c->d_dbg2 && c->gemv_dbg_slot < 1024) {
+      p.dbg = c->d_dbg2;
+      p.dbg_slot = c->gemv_dbg_slot++;
+    }
     const size_t smem = (size_t)p.n * 8 + gemv_scratch_bytes(p, c->num_sms, 1, 512, (size_t)p.n * 8);
     void* args[] = {&p};
     return launch(c, kclass, (const void*)fn, dim3(c->num_sms), dim3(512), smem, 1, args, st);
