@@ -179,6 +179,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split form: arrive early, wait later (e.g. "every CTA of the cluster has started" before the first
+// store into a peer's shared memory, without stalling at kernel entry)
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // address of `p` (a shared variable of this CTA) inside CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t dsmem_addr(const void* p, uint32_t rank) {
   uint32_t r;

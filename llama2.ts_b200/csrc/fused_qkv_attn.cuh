@@ -86,6 +86,7 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
   __shared__ double c_sum;
 
   griddep_launch_dependents();
+  cluster_arrive();   // "this CTA has started": waited for before the first store into a peer's shared memory
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank(), CS = cluster_nctarank();
@@ -212,6 +213,8 @@ __device__ __forceinline__ void qkv_attn_body(const QkvAttnParams& p) {
     }
   }
   __syncthreads();
+  cluster_wait();     // every CTA of the cluster is running (compute-sanitizer racecheck: a peer's shared memory
+                      // may only be written once that block has entered); the peers arrived at their entry
 
   {
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};

@@ -25,7 +25,8 @@ case "$what" in
             python bench.py --steps 4 --warmup 3 --no-others --no-cpu-baseline "$@" > gpurun_out/ncu_full.log 2>&1
           tail -3 gpurun_out/ncu_full.log ;;
   sanitizer) tool=$1; shift
-          timeout 900 compute-sanitizer --tool $tool --error-exitcode 0 python "$@" > gpurun_out/sanitizer_$tool.log 2>&1
-          tail -15 gpurun_out/sanitizer_$tool.log ;;
+          timeout 600 compute-sanitizer --tool $tool --print-limit 2000 --error-exitcode 0 python "$@" > gpurun_out/sanitizer_$tool.log 2>&1
+          echo "exit $?" >> gpurun_out/sanitizer_$tool.log
+          grep -c "=========" gpurun_out/sanitizer_$tool.log; tail -12 gpurun_out/sanitizer_$tool.log ;;
   *) echo "unknown: $what"; exit 2 ;;
 esac
