@@ -1714,9 +1714,13 @@ L2B_API int l2b_create_multi(const int32_t hdr[7], int32_t n_gpus, int32_t tp_de
         int can = 0;
         cudaDeviceCanAccessPeer(&can, a, b);
         if (!can) { rc = fail(nullptr, L2B_ECOMM, "device %d cannot map device %d's memory (no NVLink/P2P)", a, b); break; }
+        static bool enabled[kMaxTp][kMaxTp];   // per process: a second group must not enable it again
+        if (enabled[a][b]) continue;
         e = cudaDeviceEnablePeerAccess(b, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
           rc = fail(nullptr, L2B_ECOMM, "cudaDeviceEnablePeerAccess(%d -> %d): %s", a, b, cudaGetErrorString(e));
+        else
+          enabled[a][b] = true;
         cudaGetLastError();
       }
     }
