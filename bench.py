@@ -621,11 +621,16 @@ def main():
             ctx.reset()
             ctx.prefill(pkg.synth.teacher_tokens(p0, V, 6), 0, want_logits=False)   # fills KV rows 0..p0-1
             ctx.generate_greedy([5], [p0], 8)                                       # warm-up of this graph
-            t = ctx.generate_greedy([7], [p0 + 8], n_lc - 8 if p0 + n_lc <= S else S - p0 - 8)
+            t = ctx.generate_greedy([7], [p0 + 8], min(n_lc - 8, S - p0 - 8 - 4))
             n_run = t.shape[0]
             lc_ms = ctx.last_device_ms()
             lb = pkg.synth.step_bytes(hdr, p0 + 8 + (n_run - 1) / 2.0)
+            lc_kernels = {}
+            if p0 + 8 + n_run + 4 <= S:    # per-kernel event times at this depth (room for 4 more positions)
+                pk, _, _, _, _ = kernel_table(pkg, ctx, hdr, 1, p0 + 8 + n_run)
+                lc_kernels = {k: v["avg_us"] for k, v in pk.items()}
             line["long_context"] = {"pos_from": p0 + 8, "pos_to": p0 + 8 + n_run - 1, "tokens_per_s": n_run / (lc_ms * 1e-3),
+                                    "per_kernel_avg_us": lc_kernels,
                                     "ms_per_step": lc_ms / n_run, "bytes_per_step": lb,
                                     "kv_bytes_per_step": lb - pkg.synth.weight_bytes_per_token(hdr),
                                     "step_hbm_frac": lb / (lc_ms / n_run * 1e-3) / 1e9 / peak,

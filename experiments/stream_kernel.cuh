@@ -27,8 +27,8 @@
 #pragma once
 #include <math.h>
 
-#include "common.cuh"
-#include "decode_kernels.cuh"
+#include "../llama2.ts_b200/csrc/common.cuh"
+#include "../llama2.ts_b200/csrc/decode_kernels.cuh"
 #include "mega_kernel.cuh"
 
 namespace l2b {

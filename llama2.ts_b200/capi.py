@@ -11,7 +11,7 @@ import re
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libllama2_b200.so")
+LIB_PATH = os.environ.get("L2B_LIBRARY") or os.path.join(HERE, "libllama2_b200.so")   # override: A/B builds
 HEADER_PATH = os.path.join(HERE, "..", "include", "llama2_b200.h")
 
 # tensor ids, field order of `interface TransformerWeights` (llama2.ts:95-110)

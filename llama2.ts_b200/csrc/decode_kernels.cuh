@@ -756,7 +756,10 @@ l2b_rowpair_matvec_kernel(const __grid_constant__ GemvParams p) {
 constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / 32;
 constexpr int kAttnStages = 4;
-constexpr int kAttnStageBytes = 16384;
+constexpr int kAttnStageBytes = 16384;       // ring stage of the many-CTA (batched) launches
+constexpr int kAttnStageBytesBig = 32768;    // batch-1 launches (one cluster per head owns its SMs): 96 KB of
+                                             // cache rows in flight per CTA; at pos ~1800 the 4 x 16 KB ring capped the
+                                             // K and V passes at ~4 TB/s over 128 CTAs
 constexpr int kAttnMaxHs = 256;
 
 struct AttnParams {
@@ -770,6 +773,7 @@ struct AttnParams {
                                     // entries read ONE sequence's cache -- prompt prefill)
   int q_stride, xb_stride, xb_off;  // xb_off: column offset of head 0 (tensor-parallel slice)
   int tileT;         // time steps per ring stage
+  int stage_bytes;   // bytes per ring stage (kAttnStageBytes or kAttnStageBytesBig)
   int sc_cap;        // floats reserved for scores per CTA
   // tensor-parallel all-gather of the output slice (nullptr when tp_size == 1)
   float* peer_xb[kMaxTp];  // peers' xb replicas (including our own)
@@ -791,7 +795,7 @@ struct AttnParams {
 __global__ void __launch_bounds__(kAttnThreads, 1) l2b_attn_decode_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(128) unsigned char attn_smem_raw[];
   float* ring = reinterpret_cast<float*>(attn_smem_raw);                      // kAttnStages * stage
-  float* sc = ring + (size_t)kAttnStages * (kAttnStageBytes / 4);          // sc_cap floats
+  float* sc = ring + (size_t)kAttnStages * (p.stage_bytes / 4);            // sc_cap floats
   __shared__ __align__(8) uint64_t full_bar[kAttnStages];
   __shared__ __align__(8) uint64_t empty_bar[kAttnStages];
   __shared__ float s_red[kAttnWarps][kAttnMaxHs];
@@ -831,7 +835,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) l2b_attn_decode_kernel(const 
   const size_t head_off = (size_t)b * (size_t)p.kv_b_stride + ((size_t)h * p.steps) * hs;
   const float* kbase = p.kc + head_off + (size_t)t0 * hs;
   const float* vbase = p.vc + head_off + (size_t)t0 * hs;
-  const int stage_floats = kAttnStageBytes / 4;
+  const int stage_floats = p.stage_bytes / 4;
 
   auto issue = [&](int j) {
     const int s = j % kAttnStages;

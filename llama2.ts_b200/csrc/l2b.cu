@@ -594,7 +594,8 @@ int enqueue_step_batched(l2b_ctx* c, int B, cudaStream_t st, const BatchView& v)
       a.H = H; a.hs = hs; a.steps = c->steps;
       a.kv_b_stride = v.kv_stride;
       a.q_stride = D; a.xb_stride = D; a.xb_off = 0;
-      a.tileT = kAttnStageBytes / (hs * 4);
+      a.stage_bytes = kAttnStageBytes;
+      a.tileT = a.stage_bytes / (hs * 4);
       a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
       a.tp_size = 1;
       a.xh = c->XhD; a.xl = c->XlD; a.x_npad = c->Bpad;
@@ -747,7 +748,8 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       f.vc = c->vc + (size_t)l * kv_seq;
       f.fcr = c->fcr; f.fci = c->fci;
       f.xb = c->xb;
-      f.tileT = kAttnStageBytes / (hs * 4);
+      f.stage_bytes = kAttnStageBytesBig;
+      f.tileT = f.stage_bytes / (hs * 4);
       f.sc_cap = ((c->steps + fcs - 1) / fcs + 3) & ~3;
       f.evict_first = ef;
       f.l2_prefetch = 0;
@@ -759,7 +761,7 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       f.xb_off = R * Dl;
       f.tp_err = c->tp_err;
       for (int g = 0; g < G; ++g) f.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
-      const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
+      const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * f.stage_bytes + (size_t)f.sc_cap * 4;
       void* args[] = {&f};
       int rc = launch(c, L2B_K_QKV, (const void*)l2b_qkv_attn_tp_kernel, dim3(fcs, Hl, 1), dim3(kFThreads), smem, fcs,
                       args, st);
@@ -797,13 +799,14 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
       a.q_stride = Dl;
       a.xb_stride = D;
       a.xb_off = R * Dl;
-      a.tileT = kAttnStageBytes / (hs * 4);
+      a.stage_bytes = kAttnStageBytesBig;
+      a.tileT = a.stage_bytes / (hs * 4);
       a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
       a.tp_size = G;
       a.tp_epoch = c->tp_epoch;
       a.tp_out_idx = eA;
       for (int g = 0; g < G; ++g) a.peer_xb[g] = (float*)(c->peer[g] + c->off_xb);
-      const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
+      const size_t smem = (size_t)kAttnStages * a.stage_bytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
       int rc = launch(c, L2B_K_ATTN, (const void*)l2b_attn_decode_kernel, dim3(cs, Hl, 1), dim3(kAttnThreads), smem,
                       cs, args, st);
@@ -924,7 +927,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
   // fused q/k/v + attention: one cluster per head
   int fcs = c->opt.fuse_cluster > 0 ? c->opt.fuse_cluster : (c->H * 8 <= 96 ? 8 : 4);
   while (fcs > 1 && (c->H * fcs > c->num_sms || 3 * hs / 2 < fcs)) fcs >>= 1;
-  const size_t fuse_smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes +
+  const size_t fuse_smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytesBig +
                            (size_t)((((c->steps + fcs - 1) / fcs + 3) & ~3)) * 4;
   const bool fuse = c->opt.fuse_qkv_attn && B == 1 && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64 &&
                     fuse_smem <= 200 * 1024;
@@ -952,7 +955,8 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       f.vc = c->vc + (size_t)l * kv_layer;
       f.fcr = c->fcr; f.fci = c->fci;
       f.xb = c->xb;
-      f.tileT = kAttnStageBytes / (hs * 4);
+      f.stage_bytes = kAttnStageBytesBig;
+      f.tileT = f.stage_bytes / (hs * 4);
       f.sc_cap = ((c->steps + fcs - 1) / fcs + 3) & ~3;
       f.evict_first = ef;
       f.l2_prefetch = ef ? c->opt.l2_prefetch : 0;
@@ -969,7 +973,7 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
         c->sync_idx++;
         c->sync_prev_grid = fcs * H;
       }
-      const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * kAttnStageBytes + (size_t)f.sc_cap * 4;
+      const size_t smem = (size_t)D * 8 + (size_t)kAttnStages * f.stage_bytes + (size_t)f.sc_cap * 4;
       void* args[] = {&f};
       int rc = launch(c, L2B_K_QKV, (const void*)l2b_qkv_attn_kernel, dim3(fcs, H, 1), dim3(kFThreads), smem, fcs, args,
                       st);
@@ -1006,14 +1010,15 @@ int enqueue_step(l2b_ctx* c, int B, cudaStream_t st) {
       a.q_stride = D;
       a.xb_stride = D;
       a.xb_off = 0;
-      a.tileT = kAttnStageBytes / (hs * 4);
+      a.stage_bytes = B == 1 ? kAttnStageBytesBig : kAttnStageBytes;
+      a.tileT = a.stage_bytes / (hs * 4);
       a.sc_cap = ((c->steps + cs - 1) / cs + 3) & ~3;
       a.tp_size = 1;
       if (ef && c->opt.attn_prefetch) {
         a.pf_ptr = reinterpret_cast<const unsigned char*>(c->wo + (size_t)l * D * D);
         a.pf_bytes = (long long)D * D * sizeof(float);
       }
-      const size_t smem = (size_t)kAttnStages * kAttnStageBytes + (size_t)a.sc_cap * 4;
+      const size_t smem = (size_t)kAttnStages * a.stage_bytes + (size_t)a.sc_cap * 4;
       void* args[] = {&a};
       int rc = launch(c, L2B_K_ATTN, (const void*)l2b_attn_decode_kernel, dim3(cs, H, B),
                       dim3(kAttnThreads), smem, cs, args, st);
