@@ -820,7 +820,7 @@ def tp_parity(pkg, oracle, dist, rank, world, local_rank, ctx7, args):
         pkg.dist.connect_tp(tpc)
         one = pkg.Context(h, device=local_rank, max_steps=steps)
         pkg.synth.upload_blob(one, h, blob)
-        one.set_option("fuse_qkv_attn", 1 if world <= 2 else 0)   # the kernels the ranks run
+        one.set_option("fuse_qkv_attn", 0)   # the kernels the ranks run (stand-alone q/k/v and attention)
         ref = oracle.Model(h, blob)
         bits = True
         for p in range(steps):
@@ -842,7 +842,7 @@ def tp_parity(pkg, oracle, dist, rank, world, local_rank, ctx7, args):
     a = ctx7.generate_greedy([1], [0], n7)[:, 0]
     hdr = ctx7.hdr
     one7 = pkg.Context(hdr, device=local_rank, max_batch=1, max_steps=n7)
-    one7.set_option("fuse_qkv_attn", 1 if world <= 2 else 0)      # the kernels the ranks run
+    one7.set_option("fuse_qkv_attn", 0)      # the kernels the ranks run
     build_weights_on_gpu(pkg, one7, hdr, args.seed, "cuda:%d" % local_rank)
     b = one7.generate_greedy([1], [0], n7)[:, 0]
     lg_one = one7.read_state(pkg.capi.S_LOGITS)

@@ -721,14 +721,13 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
     cs = 8;
     while (cs > 1 && c->H * cs > c->num_sms) cs >>= 1;
   }
-  // Fused q/k/v+attention per head, measured on 7B at 2 ranks: clusters of 8 (128 CTAs) 266 tok/s --
-  // sixteen 8-CTA clusters do not all become resident at once --, clusters of 4 (64 CTAs) 309.5,
-  // stand-alone kernels 302.8.  With 4 or 8 ranks a rank owns too few heads to fill its SMs with one
-  // cluster per head: those keep the stand-alone kernels unless fuse_cluster is set explicitly.
-  int fcs = c->opt.fuse_cluster > 0 ? c->opt.fuse_cluster : (Hl * 8 <= 96 ? 8 : 4);
+  // Fused q/k/v+attention per head under tensor parallelism: only on request (fuse_cluster > 0).  A rank
+  // owns H/G heads, so one cluster per head leaves most of its SMs without weights to stream: measured on
+  // 7B, 2 ranks 327 (clusters of 4) vs 355 tok/s with the stand-alone kernels (q/k/v on all 148 SMs), 4
+  // ranks 483 vs 483 (before the larger attention ring), 8 ranks 607 vs 703.
+  int fcs = c->opt.fuse_cluster > 0 ? c->opt.fuse_cluster : 4;
   while (fcs > 1 && (Hl * fcs > c->num_sms || 3 * hs / 2 < fcs)) fcs >>= 1;
-  const bool fuse = c->opt.fuse_qkv_attn && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64 &&
-                    (G <= 2 || c->opt.fuse_cluster > 0);
+  const bool fuse = c->opt.fuse_qkv_attn && c->opt.fuse_cluster > 0 && hs % 4 == 0 && hs <= kAttnMaxHs && c->opt.f64;
   for (int l = 0; l < L; ++l) {
     const int eA = 4 * l, eB = 4 * l + 1, eC = 4 * l + 2, eD = 4 * l + 3;
     if (fuse) {  // this rank's heads: q/k/v rows + attention in one cluster kernel per head

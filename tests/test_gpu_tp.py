@@ -38,12 +38,10 @@ pkg.dist.connect_tp(ctx)
 toks = np.concatenate([[1], pkg.synth.teacher_tokens(steps - 1, V, 41)])
 single = pkg.Context(hdr, device=rank, max_steps=steps)
 pkg.synth.upload_blob(single, hdr, blob)
-# Row sharding keeps every output element's summation order, and with these shapes the fused
-# q/k/v+attention kernel splits the time steps over the same cluster size on one GPU and on a rank
-# (8 CTAs per head), so the logits are bit-identical.  More than 2 ranks keep the stand-alone
-# q/k/v and attention kernels: compare with the same kernels on one GPU.
-fused_tp = world <= 2
-single.set_option("fuse_qkv_attn", 1 if fused_tp else 0)
+# Row sharding keeps every output element's canonical summation order, so the logits are bit-identical to
+# the one-GPU library running the same kernels: a rank runs the stand-alone q/k/v and attention kernels
+# (the fused per-head cluster kernel only on request, checked at the end).
+single.set_option("fuse_qkv_attn", 0)
 ref = l2ref.Model(hdr, blob)
 l2ref.set_threads(4)
 worst, ok_bits = 0.0, True
@@ -62,12 +60,17 @@ forced = np.full(steps, -1, np.int32); forced[:3] = toks[1:4]
 a = ctx.generate_greedy([1], [0], steps, forced)[:, 0]
 b = single.generate_greedy([1], [0], steps, forced)[:, 0]
 assert np.array_equal(a, b), (rank, a, b)
-for fuse in (0, 1):                      # the stand-alone kernels on both sides: bit-identical as well
-    ctx.reset(); single.reset()
-    ctx.set_option("fuse_qkv_attn", fuse); single.set_option("fuse_qkv_attn", fuse if fused_tp else 0)
-    a2 = ctx.generate_greedy([1], [0], steps, forced)[:, 0]
-    b2 = single.generate_greedy([1], [0], steps, forced)[:, 0]
-    assert np.array_equal(a2, b2) and np.array_equal(a2, a), (rank, fuse, a2, b2)
+# the fused q/k/v+attention cluster kernel on request, the same cluster size on both sides
+ctx.reset(); single.reset()
+ctx.set_option("fuse_cluster", 4); single.set_option("fuse_cluster", 4); single.set_option("fuse_qkv_attn", 1)
+a2 = ctx.generate_greedy([1], [0], steps, forced)[:, 0]
+b2 = single.generate_greedy([1], [0], steps, forced)[:, 0]
+assert np.array_equal(a2, b2) and np.array_equal(a2, a), (rank, "fused", a2, b2)
+lt, ls = ctx.read_state(pkg.capi.S_LOGITS), single.read_state(pkg.capi.S_LOGITS)
+assert np.array_equal(lt, ls), (rank, "fused logits", np.abs(lt - ls).max())
+ctx.set_option("fuse_cluster", 0); single.set_option("fuse_cluster", 0); single.set_option("fuse_qkv_attn", 0)
+ctx.reset(); single.reset()
+ctx.generate_greedy([1], [0], steps, forced); single.generate_greedy([1], [0], steps, forced)
 ms_tp, ms_one = ctx.last_device_ms() / steps, single.last_device_ms() / steps
 dist.barrier()
 print("rank %%d ok: max|dlogit| %%.3g, bit-identical to 1 GPU, %%.3f ms/step (1 GPU %%.3f)" %% (rank, worst, ms_tp, ms_one))

@@ -21,7 +21,7 @@ one = pkg.Context(hdr, device=0, max_batch=1, max_steps=steps)
 build_weights_on_gpu(pkg, one, hdr, 0, "cuda:0")
 grp = pkg.Context(hdr, n_gpus=n, tp_degree=n, max_batch=1, max_steps=steps)
 build_weights_on_gpu(pkg, grp, hdr, 0, "cuda:0")
-one.set_option("fuse_qkv_attn", 1 if n <= 2 else 0)
+one.set_option("fuse_qkv_attn", 0)
 for mode in ({}, {"graph": 0}, {"graph": 0, "pdl": 0}):
     for k, v in mode.items():
         grp.set_option(k, v)
