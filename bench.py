@@ -676,6 +676,10 @@ def main():
     barrier()
 
     if use_tp and extras:
+        try:   # what the same exchanges would cost as NCCL calls (the baseline the in-kernel path replaces)
+            line["nccl_exchange_baseline"] = nccl_exchange_baseline(torch, dist, world, D, F, L)
+        except Exception as e:
+            line["nccl_exchange_baseline"] = {"error": str(e)}
         try:   # BASELINE configs[4]: 256 independent sequences partitioned over the N GPUs
             gb = 256
             bl = gb // world
@@ -795,6 +799,32 @@ def main():
         host_barrier()
         dist.destroy_process_group()
     return 0
+
+
+def nccl_exchange_baseline(torch, dist, world, D, F, L, iters=200):
+    """The tensor-parallel step's exchanges as stand-alone NCCL all-gathers over NVLink: 3 of D floats and 1 of
+    F floats per layer (xb, x, hb, x), launched back to back on one stream, CUDA-event timed.  The library
+    fuses these exchanges into its kernels (peer stores + sequence tags); this is the side-by-side number."""
+    out = {}
+    for name, n in (("all_gather_D_floats", D), ("all_gather_F_floats", F)):
+        src = torch.zeros(n // world, dtype=torch.float32, device="cuda")
+        dst = torch.zeros(n // world * world, dtype=torch.float32, device="cuda")
+        for _ in range(20):
+            dist.all_gather_into_tensor(dst, src)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            dist.all_gather_into_tensor(dst, src)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e3 / iters], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name + "_us"] = float(t.item())
+    out["per_token_us"] = L * (3 * out["all_gather_D_floats_us"] + out["all_gather_F_floats_us"])
+    out["note"] = ("%d NCCL all-gathers per token, back to back with nothing between them (no kernel can start before "
+                   "the gather it consumes has finished); compare with ms_per_step of the whole fused step" % (4 * L))
+    return out
 
 
 def tp_parity(pkg, oracle, dist, rank, world, local_rank, ctx7, args):
