@@ -395,10 +395,14 @@ int launch_gemv(l2b_ctx* c, int kclass, GemvParams& p, int B, cudaStream_t st) {
   return 0;
 }
 
+// CTAs per (sequence, head) of the stand-alone attention kernel: as many as fit the SMs, but no more than the
+// KV capacity the context was created for warrants (at least 64 time steps per CTA): splitting one head over
+// a cluster costs four cluster barriers + DSMEM round trips (~5 us), which only a long context pays back.
 int auto_cluster(const l2b_ctx* c, int B) {
   if (c->opt.attn_cluster > 0) return c->opt.attn_cluster;
   int cs = 8;
   while (cs > 1 && c->H * B * cs > c->num_sms) cs >>= 1;
+  while (cs > 1 && (c->steps + cs - 1) / cs < 64) cs >>= 1;
   return cs;
 }
 
@@ -717,9 +721,10 @@ int enqueue_step_tp(l2b_ctx* c, cudaStream_t st) {
 
   // same time-step split as the single-GPU launch, so the attention sums associate identically
   int cs = c->opt.attn_cluster;
-  if (cs <= 0) {
+  if (cs <= 0) {   // the rule of auto_cluster() with the MODEL's head count (not this rank's)
     cs = 8;
     while (cs > 1 && c->H * cs > c->num_sms) cs >>= 1;
+    while (cs > 1 && (c->steps + cs - 1) / cs < 64) cs >>= 1;
   }
   // Fused q/k/v+attention per head under tensor parallelism: only on request (fuse_cluster > 0).  A rank
   // owns H/G heads, so one cluster per head leaves most of its SMs without weights to stream: measured on
