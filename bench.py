@@ -491,10 +491,14 @@ def main():
     host_group = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must take the run down quickly, not leave its peers in a collective for the
+        # default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=240))
         # barriers that idle ranks sit in while ONE rank drives all the GPUs must not spin on the
         # device (an NCCL barrier kernel holds SMs; the persistent-grid kernels need all 148)
-        host_group = dist.new_group(backend="gloo")
+        host_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=600))
 
     def host_barrier():
         torch.cuda.synchronize()
