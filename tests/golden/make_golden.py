@@ -4,7 +4,8 @@
 translation with JS number semantics -- the image has no JS engine).  Run it in
 the build container (the reference is mounted read-only there):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # golden_v1.npz (tiny shapes, samplers, tokenizer)
+    python tests/golden/make_golden.py --v2     # golden_v2.npz (small / wide / stories15M shapes)
 
 The vectors pin oracle/l2ref.c (tests/test_oracle_golden.py) and, through it, the
 CUDA path.  Inputs are the seeded synthetic checkpoints of llama2.ts_b200/synth.py;
@@ -56,6 +57,52 @@ def generate_loop(R, config, state, weights, steps, prompt_tokens, temperature, 
             break
         token = nxt
     return np.array(out, dtype=np.int32), (np.array(lg, dtype=np.float32) if want_logits else None)
+
+
+OUT2 = os.path.join(ROOT, "tests", "golden", "golden_v2.npz")
+
+
+def forward_vectors(R, g, arch, seed, std, nsteps, keep_kv=True):
+    """transformer() (llama2.ts:205-303) of the reference's own text on one seeded synthetic checkpoint:
+    logits of every step, final x, the KV rows written."""
+    hdr = pkg.synth.header(arch)
+    _, blob = pkg.synth.checkpoint_blob(hdr, seed=seed, std=std)
+    key = "%s_s%d" % (arch.replace("-", "_"), seed)
+    g[key + "_hdr"] = np.array(hdr, dtype=np.int32)
+    g[key + "_std"] = np.array([std])
+    g[key + "_sha256"] = np.frombuffer(hashlib.sha256(blob.tobytes()).digest(), dtype=np.uint8)
+    config = ts_exec.make_config(hdr)
+    weights = ts_exec.make_weights(config, blob)
+    state = R["newRunState"](config)
+    V = config.vocab_size
+    toks = np.concatenate([[1], pkg.synth.teacher_tokens(nsteps - 1, V, seed)]).astype(np.int32)
+    lg = []
+    for pos in range(nsteps):
+        R["transformer"](int(toks[pos]), pos, config, state, weights)
+        lg.append(state.logits.a.copy())
+        print(key, "pos", pos, flush=True)
+    g[key + "_tokens"] = toks
+    g[key + "_logits"] = np.array(lg, dtype=np.float32)
+    g[key + "_x"] = state.x.a.copy()
+    if keep_kv:
+        L, S, D = config.n_layers, config.seq_len, config.dim
+        g[key + "_key_cache"] = state.key_cache.a.reshape(L, S, D)[:, :nsteps].copy()
+        g[key + "_value_cache"] = state.value_cache.a.reshape(L, S, D)[:, :nsteps].copy()
+    return key
+
+
+def main_v2():
+    """Round 2: the same pin at the shapes the kernels are specialised for -- `small` (head_size 32, rows of
+    one 512-float tile), `wide` (Llama-2-7B's head_size 128, rows of several tiles / K-chunks, hidden size not
+    a tile multiple, unshared classifier) and the stories15M shape itself (BASELINE configs[0]: dim 288, 6 heads
+    of 48, vocab 32000, shared classifier).  ~4 minutes of CPython."""
+    R = ts_exec.load_reference()
+    g = {}
+    forward_vectors(R, g, "small", 5, 0.05, 8)
+    forward_vectors(R, g, "wide", 6, 0.03, 4)
+    forward_vectors(R, g, "stories15M", 7, 0.05, 3)
+    np.savez_compressed(OUT2, **g)
+    print("wrote", OUT2, os.path.getsize(OUT2), "bytes,", len(g), "arrays")
 
 
 def main():
@@ -172,4 +219,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--v2" in sys.argv:
+        main_v2()
+    else:
+        main()

@@ -54,6 +54,32 @@ def test_teacher_forced_logits_and_state(pkg, oracle, arch, seed, std):
     ctx.close()
 
 
+@pytest.mark.parametrize("key,arch", [("small_s5", "small"), ("wide_s6", "wide"), ("stories15M_s7", "stories15M")])
+def test_gpu_against_reference_golden_vectors(pkg, key, arch):
+    """The CUDA path against logits / KV rows produced by EXECUTING THE REFERENCE'S OWN TEXT
+    (tests/golden/golden_v2.npz, made by tests/golden/make_golden.py --v2) -- no oracle in between."""
+    import os
+    G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
+    hdr = [int(v) for v in G2[key + "_hdr"]]
+    seed = int(key.rsplit("s", 1)[1])
+    _, blob = pkg.synth.checkpoint_blob(hdr, seed=seed, std=float(G2[key + "_std"][0]))
+    toks = G2[key + "_tokens"]
+    with pkg.Context(hdr, device=0, max_batch=1, max_steps=len(toks)) as ctx:
+        pkg.synth.upload_blob(ctx, hdr, blob)
+        worst = 0.0
+        for pos, t in enumerate(toks):
+            got = ctx.forward(int(t), pos)
+            want = G2[key + "_logits"][pos]
+            worst = max(worst, float(np.abs(got - want).max()))
+            assert close(got, want), (pos, worst)
+            assert int(np.argmax(got)) == int(np.argmax(want))
+            for l in range(hdr[2]):
+                assert close(ctx.read_state(pkg.capi.S_KEY_ROW, 0, l, pos), G2[key + "_key_cache"][l, pos])
+                assert close(ctx.read_state(pkg.capi.S_VALUE_ROW, 0, l, pos), G2[key + "_value_cache"][l, pos])
+        assert np.array_equal(ctx.forward(int(toks[0]), 0), G2[key + "_logits"][0]) or worst < 1e-5
+    print("%s vs reference-executed golden: max |dlogit| %.3g" % (arch, worst))
+
+
 def test_stories15m_shape_full_sequence(pkg, oracle):
     """BASELINE config 1 shape (dim 288, 6 layers, 6 heads of 48, seq 256), random-init,
     teacher-forced over all 256 positions."""

@@ -102,6 +102,33 @@ def test_transformer_forward_bit_exact(oracle, G, pkg, key, arch):
             assert same(m.value_row(l, pos), G[key + "_value_cache"][l, pos])
 
 
+GOLDEN2 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz")
+
+
+@pytest.mark.parametrize("key,arch", [("small_s5", "small"), ("wide_s6", "wide"), ("stories15M_s7", "stories15M")])
+def test_transformer_forward_bit_exact_at_kernel_shapes(oracle, pkg, key, arch):
+    """The same pin at the shapes the kernels are specialised for (golden_v2.npz, produced by executing the
+    reference's text): head_size 32 / 128 / 48, multi-tile rows, unshared and shared classifier, vocab 32000."""
+    G2 = np.load(GOLDEN2)
+    hdr = [int(v) for v in G2[key + "_hdr"]]
+    assert hdr == pkg.synth.header(arch)
+    seed = int(key.rsplit("s", 1)[1])
+    _, blob = pkg.synth.checkpoint_blob(hdr, seed=seed, std=float(G2[key + "_std"][0]))
+    assert hashlib.sha256(blob.tobytes()).digest() == G2[key + "_sha256"].tobytes(), \
+        "synthetic checkpoint drifted: re-run tests/golden/make_golden.py --v2"
+    m = oracle.Model(hdr, blob)
+    oracle.set_threads(4)
+    toks = G2[key + "_tokens"]
+    for pos, t in enumerate(toks):
+        assert same(m.forward(int(t), pos), G2[key + "_logits"][pos]), pos
+    oracle.set_threads(1)
+    assert same(m.x(), G2[key + "_x"])
+    for l in range(hdr[2]):
+        for pos in range(len(toks)):
+            assert same(m.key_row(l, pos), G2[key + "_key_cache"][l, pos])
+            assert same(m.value_row(l, pos), G2[key + "_value_cache"][l, pos])
+
+
 @pytest.mark.parametrize("name,temp,topp", [("greedy", 0.0, 1.0), ("sample", 1.0, 1.0), ("topp", 0.8, 0.9)])
 def test_generate_loop_matches_reference(oracle, G, pkg, name, temp, topp):
     """The generate loop (llama2.ts:460-508) incl. prompt forcing, temperature, top-p, seed 1."""
