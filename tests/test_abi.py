@@ -34,6 +34,29 @@ def test_sass_uses_bulk_copy_and_fp64(pkg):
     assert "LDG.E.128" in sass
 
 
+def test_sass_uses_tcgen05_and_tensor_memory(pkg):
+    """Evidence that the batched path runs on the 5th-generation tensor cores: tcgen05.mma (UTCHMMA) with
+    accumulators / the weight operand in tensor memory (LDTM reads, STTM writes), no mma.sync / wgmma recompiles."""
+    sass = subprocess.run(["cuobjdump", "-sass", pkg.capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("UTCHMMA") >= 16
+    assert "LDTM" in sass and "STTM" in sass
+    assert "HMMA.16816" not in sass and "WGMMA" not in sass
+
+
+def test_multi_gpu_argument_validation_needs_no_gpu(pkg):
+    """l2b_create_multi (SURVEY 8b's signature): bad n_gpus / tp_degree / max_batch are rejected before any
+    device is touched; group-only restrictions are stated in the message."""
+    lib = pkg.capi.Library.get()
+    out = C.c_void_p()
+    hdr = (C.c_int32 * 7)(64, 176, 2, 4, 4, 512, 32)
+    assert lib.dll.l2b_create_multi(hdr, 0, 1, 1, 0, C.byref(out)) == pkg.capi.EINVAL     # n_gpus 0
+    assert lib.dll.l2b_create_multi(hdr, 9, 1, 1, 0, C.byref(out)) == pkg.capi.EINVAL     # > 8
+    assert lib.dll.l2b_create_multi(hdr, 4, 2, 1, 0, C.byref(out)) == pkg.capi.EINVAL     # tp_degree not 1 / n_gpus
+    assert b"tp_degree" in lib.dll.l2b_last_error(None)
+    assert lib.dll.l2b_create_multi(hdr, 2, 2, 3, 0, C.byref(out)) == pkg.capi.EINVAL     # TP group holds one sequence
+    assert lib.dll.l2b_create_multi(None, 1, 1, 1, 0, C.byref(out)) == pkg.capi.EINVAL
+
+
 def test_no_gpu_means_loud_failure_not_cpu_fallback(pkg):
     import torch
     if torch.cuda.is_available():
