@@ -88,3 +88,13 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "l2ref" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/llama2_b200.h must compile as C99 without any C++ / CUDA / torch type."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "h.c"
+    src.write_text('#include "include/llama2_b200.h"\nint main(void) { return L2B_ABI_VERSION == 2 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", root, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
